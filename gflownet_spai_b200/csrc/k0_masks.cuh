@@ -1,0 +1,156 @@
+// K0 — action lists -> kept-edge bitmasks.
+//
+// Replaces gflownet/utils.py:315-323 (`set(actions)` + O(E) list comprehension
+// per trajectory) and the two coalesce() sorts of utils.py:348-353, :124: the
+// pattern's slots are sorted once at context creation, so "building M" for a
+// trajectory is clearing one bit per action.
+//
+// Layouts
+//   mask  u32[B][W]   slot-order bit p of trajectory b (row-major per trajectory:
+//                     all atomics of a trajectory land in one W*4-byte region)
+//   maskT u32[W][Bp]  the same bits transposed: the reward kernels put 32
+//                     trajectories on the 32 lanes of a warp, so word w of 32
+//                     consecutive trajectories is one coalesced 128-byte load.
+#pragma once
+
+#include "spai_internal.cuh"
+
+namespace spai {
+
+__global__ void k0_mask_init_kernel(uint32_t* __restrict__ mask, int64_t W, int64_t E, int64_t B) {
+  const int64_t total = W * B;
+  const uint32_t tail = (E & 31) ? ((1u << (E & 31)) - 1u) : 0xffffffffu;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t w = idx % W;
+    mask[idx] = (w == W - 1) ? tail : 0xffffffffu;
+  }
+}
+
+// grid: x = action chunks of one trajectory, y-major flattened into x as
+// blockIdx.x = b * chunks + chunk so concurrently resident blocks work on
+// neighbouring trajectories. Ids outside [0, E) (the -1 padding, the terminal
+// id, anything else) match no edge, exactly like `i not in actions_set`.
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+k0_mask_clear_kernel(const int64_t* __restrict__ actions, int64_t B, int64_t T, int64_t ld,
+                     const int32_t* __restrict__ edge_slot, int64_t E,
+                     uint32_t* __restrict__ mask, int64_t W, int64_t chunks) {
+  const int64_t b = blockIdx.x / chunks;
+  const int64_t chunk = blockIdx.x % chunks;
+  if (b >= B) return;
+  const int64_t* row = actions + b * ld;
+  uint32_t* mrow = mask + b * W;
+  const int64_t t0 = chunk * (256 * UNROLL) + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const int64_t t = t0 + (int64_t)u * 256;
+    if (t < T) {
+      const int64_t a = __ldcs(row + t);          // streamed once
+      if ((uint64_t)a < (uint64_t)E) {
+        const int s = edge_slot ? __ldg(edge_slot + a) : (int)a;
+        atomicAnd(mrow + (s >> 5), ~(1u << (s & 31)));
+      }
+    }
+  }
+}
+
+// taken u32[B][ld] in EDGE order (bit set = edge removed) -> mask u32[B][W] in
+// slot order (bit set = kept).
+__global__ void k0_mask_from_taken_kernel(const uint32_t* __restrict__ taken, int64_t ld,
+                                          const int32_t* __restrict__ slot_edge, int64_t E,
+                                          uint32_t* __restrict__ mask, int64_t W, int64_t B) {
+  const int64_t total = W * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / W, w = idx % W;
+    const uint32_t tail = (w == W - 1 && (E & 31)) ? ((1u << (E & 31)) - 1u) : 0xffffffffu;
+    uint32_t out;
+    if (!slot_edge) {
+      out = ~taken[b * ld + w] & tail;
+    } else {
+      out = 0;
+      const int64_t p0 = w * 32;
+      for (int j = 0; j < 32 && p0 + j < E; ++j) {
+        const int e = __ldg(slot_edge + p0 + j);
+        const uint32_t t = taken[b * ld + (e >> 5)];
+        out |= (((t >> (e & 31)) & 1u) ^ 1u) << j;
+      }
+    }
+    mask[idx] = out;
+  }
+}
+
+// mask u32[B][W] -> maskT u32[W][Bp]; columns b in [B, Bp) are written as 0.
+__global__ void __launch_bounds__(256)
+k0_transpose_kernel(const uint32_t* __restrict__ mask, int64_t B, int64_t W,
+                    uint32_t* __restrict__ maskT, int64_t Bp) {
+  __shared__ uint32_t tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t w0 = (int64_t)blockIdx.x * 32, b0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t b = b0 + r, w = w0 + tx;
+    tile[r][tx] = (b < B && w < W) ? mask[b * W + w] : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t w = w0 + r, b = b0 + tx;
+    if (w < W && b < Bp) maskT[w * Bp + b] = tile[tx][r];
+  }
+}
+
+// nnz(M) per trajectory = kept slots, minus the surplus of repeated coordinates
+// (coalesce() merges them, preconditioner.py:71 counts stored entries).
+__global__ void __launch_bounds__(256)
+k0_popcount_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t B,
+                   long long* __restrict__ nnz) {
+  const int64_t b = blockIdx.x;
+  if (b >= B) return;
+  long long s = 0;
+  for (int64_t w = threadIdx.x; w < W; w += blockDim.x) s += __popc(mask[b * W + w]);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ long long part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    nnz[b] = t;
+  }
+}
+
+__global__ void k0_dup_correction_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t B,
+                                         const int32_t* __restrict__ dup_start,
+                                         const int32_t* __restrict__ dup_len, int64_t ndup,
+                                         long long* __restrict__ nnz) {
+  const int64_t total = ndup * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / ndup, g = idx % ndup;
+    int kept = 0;
+    const int s0 = dup_start[g];
+    for (int j = 0; j < dup_len[g]; ++j) {
+      const int s = s0 + j;
+      kept += (mask[b * W + (s >> 5)] >> (s & 31)) & 1u;
+    }
+    if (kept > 1) atomicAdd((unsigned long long*)(nnz + b), (unsigned long long)(-(long long)(kept - 1)));
+  }
+}
+
+// slot-order mask -> EDGE-order bytes (the reference's `remaining_edges_mask`
+// as a 0/1 vector, gflownet/utils.py:323).
+__global__ void k0_kept_bytes_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t B,
+                                     const int32_t* __restrict__ edge_slot, int64_t E,
+                                     uint8_t* __restrict__ out) {
+  const int64_t total = E * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / E, e = idx % E;
+    const int s = edge_slot ? edge_slot[e] : (int)e;
+    out[idx] = (uint8_t)((mask[b * W + (s >> 5)] >> (s & 31)) & 1u);
+  }
+}
+
+}  // namespace spai

@@ -1,0 +1,289 @@
+// K2 — batched small dense Householder-QR least squares ("ls" mode, the SPAI
+// re-solve named by BASELINE.json's north star; the reference has no such code).
+//
+// For row i with kept candidate columns J (a subset of the row's candidate
+// slots) and union index set I_i the problem is
+//     min_m || A(J, I_i)^T m - e_i(I_i) ||_2 ,      row residual^2 = ||.||^2
+// (+1 if i is not in I_i: the uncovered diagonal of -I; added by the finalize
+// kernel through rows_missing_diag).
+//
+// Register kernel (k2_ls_kernel): the trajectory-independent dense tile
+// D = A(S_i, I_i)^T (|I_i| x k, gathered by K1) is staged once per (block, row)
+// in shared memory; a group of G lanes owns one (row, trajectory) problem with
+// the tile's rows distributed cyclically over the G lanes and held in registers
+// (QL rows x KMAX columns per lane, statically indexed). Columns of removed
+// candidates are zeroed by the kept-mask, which leaves the least-squares
+// residual unchanged; reflectors of zero / dependent columns are skipped and the
+// pivot row p advances only on active columns. Column norms and v^T a_c dot
+// products are reduced over the G lanes with xor-shuffles. All FP64/FP32 CUDA
+// cores; the tiles (<= 64 x 32) are far too small for tensor-core MMA shapes.
+//
+// Generic kernel (k2_ls_generic_kernel): one warp per problem with the compacted
+// tile in a global scratch slab — any |I_i| and k, used for the rows outside the
+// register kernels' classes.
+#pragma once
+
+#include <utility>
+
+#include "spai_internal.cuh"
+
+namespace spai {
+
+template <int G> __device__ __forceinline__ float k2_gsum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G> __device__ __forceinline__ double k2_gsum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> struct K2Tol;
+template <> struct K2Tol<float>  { static constexpr float  v = 1e-10f; };   // (~85 eps)^2
+template <> struct K2Tol<double> { static constexpr double v = 1e-26;  };   // (~450 eps)^2
+
+// One Householder step on column E of the lane-distributed tile. E is a
+// template parameter so that every register-array index is a compile-time
+// constant (a runtime column loop would demote `a` to local memory).
+template <typename T, int KMAX, int G, int QL, int E>
+__device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p,
+                                        const T* __restrict__ coln2, int lg) {
+  T sig = T(0), alp = T(0);
+#pragma unroll
+  for (int t = 0; t < QL; ++t) {
+    const int r = t * G + lg;
+    const T v = (r >= p) ? a[t][E] : T(0);
+    sig = fma(v, v, sig);
+    alp += (r == p) ? v : T(0);
+  }
+  sig = k2_gsum<G>(sig);
+  alp = k2_gsum<G>(alp);
+  const bool act = sig > coln2[E] * K2Tol<T>::v;
+  const T nrm = sqrt(sig);
+  const T beta = (alp >= T(0)) ? -nrm : nrm;
+  const T inv = act ? T(1) / (sig - alp * beta) : T(0);
+  T vt[QL];
+#pragma unroll
+  for (int t = 0; t < QL; ++t) {
+    const int r = t * G + lg;
+    vt[t] = (r > p) ? a[t][E] : ((r == p) ? alp - beta : T(0));
+  }
+#pragma unroll
+  for (int c = E + 1; c < KMAX; ++c) {
+    T dot = T(0);
+#pragma unroll
+    for (int t = 0; t < QL; ++t) dot = fma(vt[t], a[t][c], dot);
+    dot = k2_gsum<G>(dot);
+    const T f = dot * inv;
+#pragma unroll
+    for (int t = 0; t < QL; ++t) a[t][c] = fma(-f, vt[t], a[t][c]);
+  }
+  {
+    T dot = T(0);
+#pragma unroll
+    for (int t = 0; t < QL; ++t) dot = fma(vt[t], y[t], dot);
+    dot = k2_gsum<G>(dot);
+    const T f = dot * inv;
+#pragma unroll
+    for (int t = 0; t < QL; ++t) y[t] = fma(-f, vt[t], y[t]);
+  }
+  p += act ? 1 : 0;
+}
+
+template <typename T, int KMAX, int G, int QL, int... Es>
+__device__ __forceinline__ void k2_all_steps(T (&a)[QL][KMAX], T (&y)[QL], int& p,
+                                             const T* __restrict__ coln2, int lg,
+                                             std::integer_sequence<int, Es...>) {
+  (k2_step<T, KMAX, G, QL, Es>(a, y, p, coln2, lg), ...);
+}
+
+constexpr int K2_NW = 4;          // warps per block
+constexpr int K2_MAX_NTG = 16;    // trajectories per lane group
+
+template <typename T, int KMAX, int G, int QL>
+__global__ void __launch_bounds__(K2_NW * 32)
+k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
+             const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
+             const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
+             int64_t Bp, int ntg, double* __restrict__ partial) {
+  using Rec = typename RecOf<T>::type;
+  constexpr int QP = QL * G;
+  constexpr int NG = 32 / G;
+  constexpr int NTHREADS = K2_NW * 32;
+  constexpr int GROUPS = K2_NW * NG;
+  __shared__ __align__(16) T tile[QP * KMAX];
+  __shared__ T coln2[KMAX];
+  __shared__ double totsm[K2_MAX_NTG * GROUPS];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int grp = lane / G, lg = lane % G;
+  const int gid = warp * NG + grp;
+  const int64_t bbase = (int64_t)blockIdx.y * ((int64_t)GROUPS * ntg);
+
+  for (int x = tid; x < K2_MAX_NTG * GROUPS; x += NTHREADS) totsm[x] = 0.0;
+
+  const int64_t ri0 = nrows * blockIdx.x / gridDim.x;
+  const int64_t ri1 = nrows * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t ri = ri0; ri < ri1; ++ri) {
+    const int i = rows[ri];
+    const int64_t cb = cptr[i], ce = cptr[i + 1];
+    const int sp = sptr[i];
+    const int k = sptr[i + 1] - sp;
+    const int diag = r_diag[i];
+    __syncthreads();
+    for (int x = tid; x < QP * KMAX; x += NTHREADS) tile[x] = T(0);
+    __syncthreads();
+    for (int64_t c = cb + tid; c < ce; c += NTHREADS) {
+      const Rec r = recs[c];
+      tile[rec_s(r.flags) * KMAX + rec_e(r.flags)] = rec_a(r);
+    }
+    __syncthreads();
+    if (tid < KMAX) {
+      T s = T(0);
+      for (int q = 0; q < QP; ++q) { const T v = tile[q * KMAX + tid]; s = fma(v, v, s); }
+      coln2[tid] = s;
+    }
+    __syncthreads();
+
+    const int64_t w0 = sp >> 5;
+    const int sh = sp & 31;
+    const bool two = sh + k > 32;
+    const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+
+#pragma unroll 1
+    for (int j = 0; j < ntg; ++j) {
+      int64_t b = bbase + (int64_t)j * GROUPS + gid;
+      if (b >= Bp) b = 0;                       // result discarded below
+      const uint32_t lo = maskT[w0 * Bp + b];
+      const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
+      const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
+
+      T a[QL][KMAX];
+      T y[QL];
+#pragma unroll
+      for (int t = 0; t < QL; ++t) {
+        const int r = t * G + lg;
+#pragma unroll
+        for (int e = 0; e < KMAX; ++e) a[t][e] = ((m >> e) & 1u) ? tile[r * KMAX + e] : T(0);
+        y[t] = (r == diag) ? T(1) : T(0);
+      }
+      int p = 0;
+      k2_all_steps<T, KMAX, G, QL>(a, y, p, coln2, lg, std::make_integer_sequence<int, KMAX>{});
+      T r2 = T(0);
+#pragma unroll
+      for (int t = 0; t < QL; ++t) {
+        const int r = t * G + lg;
+        r2 += (r >= p) ? y[t] * y[t] : T(0);
+      }
+      r2 = k2_gsum<G>(r2);
+      if (lg == 0) totsm[j * GROUPS + gid] += (double)r2;
+    }
+  }
+  __syncthreads();
+  for (int x = tid; x < ntg * GROUPS; x += NTHREADS) {
+    const int j = x / GROUPS, g = x % GROUPS;
+    const int64_t b = bbase + (int64_t)j * GROUPS + g;
+    if (b < Bp) partial[(int64_t)blockIdx.x * Bp + b] = totsm[x];
+  }
+}
+
+// ---------------------------------------------------------------- generic path
+// One warp per (row, trajectory). Scratch per warp: kk columns of q entries
+// (column-major) + y[q]. Any k (kept bits fetched word by word) and any q.
+template <typename T>
+__device__ __forceinline__ T k2_wsum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
+                     const int64_t* __restrict__ cptr, const int32_t* __restrict__ sptr,
+                     const int32_t* __restrict__ r_q, const int32_t* __restrict__ r_diag,
+                     const int32_t* __restrict__ rows, int64_t nrows,
+                     const uint32_t* __restrict__ maskT, int64_t Bp, int64_t B, T* work,
+                     int64_t work_stride, int32_t* colmap, int64_t colmap_stride,
+                     double* __restrict__ res2) {
+  using Rec = typename RecOf<T>::type;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  T* A = work + warp * work_stride;
+  int32_t* cmap = colmap + warp * colmap_stride;
+  const int64_t items = nrows * B;
+  for (int64_t it = warp; it < items; it += nwarps) {
+    const int64_t ri = it / B, b = it % B;
+    const int i = rows[ri];
+    const int q = r_q[i];
+    const int sp = sptr[i];
+    const int k = sptr[i + 1] - sp;
+    const int diag = r_diag[i];
+    const int64_t cb = cptr[i], ce = cptr[i + 1];
+    if (q == 0) continue;                        // nothing gathered: row adds only the constant
+    // compact the kept columns: cmap[e] = column index or -1
+    int kk = 0;
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const int e = e0 + lane;
+      bool kept = false;
+      if (e < k) {
+        const int64_t bit = (int64_t)sp + e;
+        kept = (maskT[(bit >> 5) * Bp + b] >> (bit & 31)) & 1u;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, kept);
+      if (e < k) cmap[e] = kept ? kk + __popc(bal & ((1u << lane) - 1u)) : -1;
+      kk += __popc(bal);
+    }
+    T* y = A + (int64_t)kk * q;
+    for (int64_t x = lane; x < (int64_t)kk * q + q; x += 32) A[x] = T(0);
+    __syncwarp();
+    for (int64_t c = cb + lane; c < ce; c += 32) {
+      const Rec r = recs[c];
+      const int col = cmap[rec_e(r.flags)];
+      if (col >= 0) A[(int64_t)col * q + rec_s(r.flags)] = rec_a(r);
+    }
+    if (lane == 0 && diag >= 0) y[diag] = T(1);
+    __syncwarp();
+    int p = 0;
+    for (int j = 0; j < kk && p < q; ++j) {
+      T* aj = A + (int64_t)j * q;
+      T full = T(0), sig = T(0);
+      for (int r = lane; r < q; r += 32) {
+        const T v = aj[r];
+        full = fma(v, v, full);
+        if (r >= p) sig = fma(v, v, sig);
+      }
+      full = k2_wsum(full);
+      sig = k2_wsum(sig);
+      if (!(sig > full * K2Tol<T>::v)) continue;          // dependent / zero column
+      const T alp = aj[p];
+      const T nrm = sqrt(sig);
+      const T beta = (alp >= T(0)) ? -nrm : nrm;
+      const T inv = T(1) / (sig - alp * beta);
+      __syncwarp();
+      if (lane == 0) aj[p] = alp - beta;
+      __syncwarp();
+      for (int c = j + 1; c <= kk; ++c) {                  // c == kk is the right-hand side
+        T* ac = A + (int64_t)c * q;
+        T dot = T(0);
+        for (int r = p + lane; r < q; r += 32) dot = fma(aj[r], ac[r], dot);
+        dot = k2_wsum(dot);
+        const T f = dot * inv;
+        for (int r = p + lane; r < q; r += 32) ac[r] = fma(-f, aj[r], ac[r]);
+      }
+      __syncwarp();
+      ++p;
+    }
+    T r2 = T(0);
+    for (int r = p + lane; r < q; r += 32) r2 = fma(y[r], y[r], r2);
+    r2 = k2_wsum(r2);
+    if (lane == 0) atomicAdd(res2 + b, (double)r2);
+    __syncwarp();
+  }
+}
+
+}  // namespace spai

@@ -1,0 +1,917 @@
+// libspai_b200.so — C-ABI host side of the B200-native SPAI reward path.
+// Declarations and the reference interfaces they replace: include/spai_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "k0_masks.cuh"
+#include "k1_plan.cuh"
+#include "k2_ls.cuh"
+#include "k3_copy.cuh"
+#include "k4_sample.cuh"
+#include "spai_internal.cuh"
+
+namespace spai {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct Arena {      // owns device allocations of one object
+  std::vector<void*> ptrs;
+  int64_t bytes = 0;
+  template <typename T> int alloc(T** out, int64_t count) {
+    void* p = nullptr;
+    const size_t sz = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", sz, cudaGetErrorString(e));
+      cudaGetLastError();
+      return SPAI_ERR_NOMEM;
+    }
+    ptrs.push_back(p);
+    bytes += (int64_t)sz;
+    *out = reinterpret_cast<T*>(p);
+    return SPAI_OK;
+  }
+  template <typename T> int upload(T** out, const std::vector<T>& h) {
+    SPAI_TRY(alloc(out, (int64_t)h.size()));
+    if (!h.empty()) SPAI_CUDA(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SPAI_OK;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+  }
+  ~Arena() { release(); }
+};
+
+// ------------------------------------------------------------------ host side
+struct HostPattern {
+  std::vector<int32_t> sptr, slot_col, slot_edge, edge_slot, dup_start, dup_len;
+  std::vector<float> val32;
+  std::vector<double> val64;
+};
+struct HostCsr {
+  std::vector<int32_t> ptr, col;
+  std::vector<float> val32;
+  std::vector<double> val64;
+};
+
+static int sort_coo(int64_t n, int64_t nnz, const int64_t* row, const int64_t* col,
+                    std::vector<int64_t>& order, std::vector<int64_t>& key, const char* what) {
+  if (nnz >= (int64_t)2147483000LL) { set_error("%s: too many entries (%lld)", what, (long long)nnz); return SPAI_ERR_UNSUPPORTED; }
+  key.resize(nnz);
+  order.resize(nnz);
+  bool sorted = true;
+  for (int64_t p = 0; p < nnz; ++p) {
+    if (row[p] < 0 || row[p] >= n || col[p] < 0 || col[p] >= n) {
+      set_error("%s: entry %lld has index (%lld, %lld) outside [0, %lld)", what, (long long)p,
+                (long long)row[p], (long long)col[p], (long long)n);
+      return SPAI_ERR_INVALID;
+    }
+    key[p] = row[p] * n + col[p];
+    order[p] = p;
+    if (p && key[p] < key[p - 1]) sorted = false;
+  }
+  if (!sorted)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+  return SPAI_OK;
+}
+
+static int build_host_pattern(int64_t n, int64_t E, const int64_t* row, const int64_t* col,
+                              const double* val, HostPattern& h, Pattern& P) {
+  std::vector<int64_t> order, key;
+  SPAI_TRY(sort_coo(n, E, row, col, order, key, "initial matrix"));
+  h.sptr.assign(n + 1, 0);
+  h.slot_col.resize(E); h.slot_edge.resize(E); h.edge_slot.resize(E);
+  h.val32.resize(E); h.val64.resize(E);
+  bool ident = true;
+  int64_t groups = 0;
+  for (int64_t p = 0; p < E; ++p) {
+    const int64_t e = order[p];
+    if (e != p) ident = false;
+    h.sptr[row[e] + 1]++;
+    h.slot_col[p] = (int32_t)col[e];
+    h.slot_edge[p] = (int32_t)e;
+    h.edge_slot[e] = (int32_t)p;
+    h.val64[p] = val[e];
+    h.val32[p] = (float)val[e];
+    if (p == 0 || key[order[p]] != key[order[p - 1]]) {
+      ++groups;
+    } else {
+      if (!h.dup_start.empty() && h.dup_start.back() + h.dup_len.back() == p) h.dup_len.back()++;
+      else { h.dup_start.push_back((int32_t)(p - 1)); h.dup_len.push_back(2); }
+    }
+  }
+  int maxk = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    maxk = std::max(maxk, h.sptr[i + 1]);
+    h.sptr[i + 1] += h.sptr[i];
+  }
+  if (maxk > MAX_ROW_SLOTS) { set_error("a row of the initial matrix has %d entries (max %d)", maxk, MAX_ROW_SLOTS); return SPAI_ERR_UNSUPPORTED; }
+  P.n = n; P.E = E; P.init_nnz = groups; P.max_k = maxk; P.identity_perm = ident;
+  P.ndup = (int64_t)h.dup_start.size();
+  return SPAI_OK;
+}
+
+static int upload_pattern(Arena& ar, const HostPattern& h, Pattern& P) {
+  SPAI_TRY(ar.upload(&P.sptr, h.sptr));
+  SPAI_TRY(ar.upload(&P.slot_col, h.slot_col));
+  SPAI_TRY(ar.upload(&P.slot_edge, h.slot_edge));
+  SPAI_TRY(ar.upload(&P.edge_slot, h.edge_slot));
+  SPAI_TRY(ar.upload(&P.slot_val32, h.val32));
+  SPAI_TRY(ar.upload(&P.slot_val64, h.val64));
+  SPAI_TRY(ar.upload(&P.dup_start, h.dup_start));
+  SPAI_TRY(ar.upload(&P.dup_len, h.dup_len));
+  return SPAI_OK;
+}
+
+static int build_host_csr(int64_t n, int64_t nnz, const int64_t* row, const int64_t* col,
+                          const double* val, HostCsr& h) {
+  std::vector<int64_t> order, key;
+  SPAI_TRY(sort_coo(n, nnz, row, col, order, key, "original matrix"));
+  h.ptr.assign(n + 1, 0);
+  h.col.clear(); h.val32.clear(); h.val64.clear();
+  h.col.reserve(nnz); h.val32.reserve(nnz); h.val64.reserve(nnz);
+  for (int64_t p = 0; p < nnz; ++p) {
+    const int64_t e = order[p];
+    if (p && key[order[p]] == key[order[p - 1]]) {        // coalesce: sum in stored order
+      h.val64.back() += val[e];
+      h.val32.back() += (float)val[e];
+    } else {
+      h.ptr[row[e] + 1]++;
+      h.col.push_back((int32_t)col[e]);
+      h.val64.push_back(val[e]);
+      h.val32.push_back((float)val[e]);
+    }
+  }
+  for (int64_t i = 0; i < n; ++i) h.ptr[i + 1] += h.ptr[i];
+  return SPAI_OK;
+}
+
+static int upload_csr(Arena& ar, const HostCsr& h, int64_t n, int64_t stored, CsrA& A) {
+  A.n = n; A.nnz = (int64_t)h.col.size(); A.nnz_stored = stored;
+  SPAI_TRY(ar.upload(&A.ptr, h.ptr));
+  SPAI_TRY(ar.upload(&A.col, h.col));
+  SPAI_TRY(ar.upload(&A.val32, h.val32));
+  SPAI_TRY(ar.upload(&A.val64, h.val64));
+  return SPAI_OK;
+}
+
+// ls register-kernel classes: {KMAX, G, QL, available for f64}
+struct LsClass { int kmax, g, ql; bool f64; };
+static const LsClass kLsClasses[LS_NCLASS - 1] = {
+    {8, 4, 5, true}, {8, 8, 5, true}, {16, 16, 3, true}, {16, 32, 3, true},
+    {32, 32, 2, true}, {32, 32, 4, false}, {0, 0, 0, false}};
+
+static int classify_row(int k, int q, int dtype) {
+  for (int c = 0; c < LS_NCLASS - 1; ++c) {
+    const LsClass& L = kLsClasses[c];
+    if (L.kmax == 0) continue;
+    if (dtype == SPAI_F64 && !L.f64) continue;
+    if (k <= L.kmax && q <= L.g * L.ql) return c;
+  }
+  return LS_GENERIC;
+}
+
+// K1 driver: count -> scan (host) -> fill -> classify/tiling (host)
+static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const CsrA& A,
+                      const HostCsr& ha, int dtype, bool want_ls, Plan& plan, cudaStream_t st) {
+  const int64_t n = P.n;
+  plan.dtype = dtype; plan.n = n;
+  int64_t* counts = nullptr;
+  Arena tmp;
+  SPAI_TRY(tmp.alloc(&counts, n));
+  k1_count_kernel<<<(unsigned)ceil_div(std::max<int64_t>(n, 1), 256), 256, 0, st>>>(n, P.sptr, P.slot_col, A.ptr, counts);
+  SPAI_CUDA(cudaGetLastError());
+  std::vector<int64_t> hc(n);
+  SPAI_CUDA(cudaMemcpyAsync(hc.data(), counts, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaStreamSynchronize(st));
+  plan.cptr_host.assign(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (hc[i] >= (int64_t)1 << 30) { set_error("row %lld gathers %lld entries (unsupported)", (long long)i, (long long)hc[i]); return SPAI_ERR_UNSUPPORTED; }
+    plan.cptr_host[i + 1] = plan.cptr_host[i] + hc[i];
+  }
+  plan.nc = plan.cptr_host[n];
+  SPAI_TRY(ar.upload(&plan.cptr, plan.cptr_host));
+  SPAI_TRY(ar.alloc(&plan.c_col, plan.nc));
+  SPAI_TRY(ar.alloc(&plan.r_q, n));
+  SPAI_TRY(ar.alloc(&plan.r_diag, n));
+  if (dtype == SPAI_F32) {
+    Rec32* r = nullptr;
+    SPAI_TRY(ar.alloc(&r, plan.nc));
+    plan.rec_copy = r; plan.rec_ls = r;
+  } else {
+    Rec64* r = nullptr;
+    SPAI_TRY(ar.alloc(&r, plan.nc));
+    plan.rec_copy = r;
+    if (want_ls) { Rec64* l = nullptr; SPAI_TRY(ar.alloc(&l, plan.nc)); plan.rec_ls = l; }
+  }
+  if (n > 0) {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 8), 148 * 64);
+    if (dtype == SPAI_F32)
+      k1_fill_kernel<float><<<blocks, 256, 0, st>>>(n, P.sptr, P.slot_col, P.slot_val32, A.ptr, A.col, A.val32,
+                                                   plan.cptr, plan.c_col, plan.rec_copy, nullptr, plan.r_q, plan.r_diag);
+    else
+      k1_fill_kernel<double><<<blocks, 256, 0, st>>>(n, P.sptr, P.slot_col, P.slot_val64, A.ptr, A.col, A.val64,
+                                                    plan.cptr, plan.c_col, plan.rec_copy, plan.rec_ls, plan.r_q, plan.r_diag);
+    SPAI_CUDA(cudaGetLastError());
+  }
+  std::vector<int32_t> hq(n), hd(n);
+  SPAI_CUDA(cudaMemcpyAsync(hq.data(), plan.r_q, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaMemcpyAsync(hd.data(), plan.r_diag, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaStreamSynchronize(st));
+
+  // tiles of <= K3_TILE_C records (an oversized row is a tile of its own)
+  std::vector<int32_t> tiles;
+  tiles.push_back(0);
+  int64_t acc = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t c = hc[i];
+    if (acc > 0 && acc + c > K3_TILE_C) { tiles.push_back((int32_t)i); acc = 0; }
+    acc += c;
+    if (i - tiles.back() >= 4096) { tiles.push_back((int32_t)(i + 1)); acc = 0; }
+  }
+  if (tiles.back() != n) tiles.push_back((int32_t)n);
+  plan.ntiles = (int)tiles.size() - 1;
+  SPAI_TRY(ar.upload(&plan.tile_row, tiles));
+
+  std::vector<int32_t> cls[LS_NCLASS];
+  plan.rows_missing_diag = 0; plan.max_q = 0;
+  plan.generic_max_q = plan.generic_max_k = 0;
+  const double w = (dtype == SPAI_F32) ? 4.0 : 8.0;
+  double g = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int k = hp.sptr[i + 1] - hp.sptr[i];
+    const int q = hq[i];
+    if (q >= MAX_ROW_UNION) { set_error("row %lld has a union index set of %d columns (max %d)", (long long)i, q, MAX_ROW_UNION - 1); return SPAI_ERR_UNSUPPORTED; }
+    if (hd[i] < 0) plan.rows_missing_diag++;
+    plan.max_q = std::max(plan.max_q, q);
+    g += k * (4.0 + w + 8.0) + (double)hc[i] * (4.0 + w);
+    if (q == 0) continue;
+    const int c = classify_row(k, q, dtype);
+    cls[c].push_back((int32_t)i);
+    if (c == LS_GENERIC) {
+      plan.generic_max_q = std::max<int64_t>(plan.generic_max_q, q);
+      plan.generic_max_k = std::max<int64_t>(plan.generic_max_k, k);
+    }
+  }
+  plan.g_bytes_full = g;
+  for (int c = 0; c < LS_NCLASS; ++c) {
+    plan.class_count[c] = (int64_t)cls[c].size();
+    if (want_ls && !cls[c].empty()) SPAI_TRY(ar.upload(&plan.class_rows[c], cls[c]));
+  }
+  (void)ha;
+  plan.bytes = ar.bytes;
+  return SPAI_OK;
+}
+
+// ------------------------------------------------------------------ evaluation
+struct Workspace {
+  void* base = nullptr;
+  int64_t bytes = 0;
+  int ensure(int64_t need) {
+    if (need <= bytes) return SPAI_OK;
+    if (base) cudaFree(base);
+    base = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&base, (size_t)need);
+    if (e != cudaSuccess) { set_error("workspace cudaMalloc(%lld) failed: %s", (long long)need, cudaGetErrorString(e)); cudaGetLastError(); return SPAI_ERR_NOMEM; }
+    bytes = need;
+    return SPAI_OK;
+  }
+  ~Workspace() { if (base) cudaFree(base); }
+};
+
+struct Carver {
+  char* p; char* end;
+  template <typename T> T* take(int64_t count) {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255);
+    T* out = reinterpret_cast<T*>(a);
+    p = reinterpret_cast<char*>(a) + count * (int64_t)sizeof(T);
+    return out;
+  }
+};
+static inline int64_t padded(int64_t bytes) { return round_up(bytes, 256) + 256; }
+
+struct EvalShape {       // launch geometry of one reward evaluation over Bp trajectories
+  int nt = 1, gx = 1, gy = 1;                       // copy kernel
+  int ls_gx[LS_NCLASS] = {}, ls_gy[LS_NCLASS] = {}, ls_ntg[LS_NCLASS] = {};
+  int parts = 1;
+  int64_t generic_work = 0, generic_cmap = 0, generic_warps = 0;
+};
+
+static EvalShape plan_shape(const Plan& plan, int mode, int64_t Bp, int sm_count) {
+  EvalShape s;
+  if (mode == SPAI_MODE_COPY) {
+    s.nt = (Bp >= 2048) ? 4 : (Bp >= 512 ? 2 : 1);
+    s.gy = (int)ceil_div(Bp, (int64_t)K3_THREADS * s.nt);
+    const int target = sm_count * 8;
+    s.gx = (int)std::max<int64_t>(1, std::min<int64_t>(plan.ntiles, std::max(1, target / s.gy)));
+    s.parts = s.gx;
+  } else {
+    s.parts = 0;
+    for (int c = 0; c < LS_NCLASS - 1; ++c) {
+      if (!plan.class_count[c]) continue;
+      const LsClass& L = kLsClasses[c];
+      const int groups = K2_NW * (32 / L.g);
+      s.ls_ntg[c] = (int)std::min<int64_t>(K2_MAX_NTG, ceil_div(Bp, groups));
+      s.ls_gy[c] = (int)ceil_div(Bp, (int64_t)groups * s.ls_ntg[c]);
+      const int target = sm_count * 12;
+      s.ls_gx[c] = (int)std::max<int64_t>(1, std::min<int64_t>(plan.class_count[c], std::max(1, target / s.ls_gy[c])));
+      s.parts += s.ls_gx[c];
+    }
+    if (plan.class_count[LS_GENERIC]) {
+      s.generic_warps = (int64_t)sm_count * 16;
+      s.generic_work = plan.generic_max_q * (plan.generic_max_k + 1);
+      s.generic_cmap = plan.generic_max_k;
+    }
+    if (s.parts == 0) s.parts = 1;
+  }
+  return s;
+}
+
+static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int64_t Bp, int dtype) {
+  int64_t b = padded(W * Bp * 4)              // maskT
+              + padded(Bp * 8)                 // nnz
+              + padded((int64_t)s.parts * Bp * 8)
+              + padded(Bp * 8);                // res2 extra
+  if (s.generic_warps) {
+    b += padded(s.generic_warps * s.generic_work * (dtype == SPAI_F32 ? 4 : 8));
+    b += padded(s.generic_warps * s.generic_cmap * 4);
+  }
+  (void)plan;
+  return b;
+}
+
+template <typename T>
+static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const EvalShape& s,
+                           const uint32_t* maskT, int64_t Bp, double* partial, cudaStream_t st) {
+  using Rec = typename RecOf<T>::type;
+  const Rec* recs = reinterpret_cast<const Rec*>(plan.rec_ls);
+  const dim3 grid(s.ls_gx[c], s.ls_gy[c]);
+  const dim3 block(K2_NW * 32);
+#define SPAI_LS_CASE(IDX, KMAX, G, QL)                                                         \
+  case IDX:                                                                                    \
+    k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
+        plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial);             \
+    break;
+  switch (c) {
+    SPAI_LS_CASE(0, 8, 4, 5)
+    SPAI_LS_CASE(1, 8, 8, 5)
+    SPAI_LS_CASE(2, 16, 16, 3)
+    SPAI_LS_CASE(3, 16, 32, 3)
+    SPAI_LS_CASE(4, 32, 32, 2)
+    case 5:
+      if constexpr (sizeof(T) == 4) {
+        k2_ls_kernel<T, 32, 32, 4><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,
+            plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial);
+      }
+      break;
+    default: set_error("bad ls class %d", c); return SPAI_ERR_INVALID;
+  }
+#undef SPAI_LS_CASE
+  SPAI_CUDA(cudaGetLastError());
+  return SPAI_OK;
+}
+
+struct PhaseTimer {
+  bool on = false;
+  cudaEvent_t ev[5] = {};
+  int init() {
+    for (auto& e : ev) SPAI_CUDA(cudaEventCreate(&e));
+    return SPAI_OK;
+  }
+  void destroy() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+};
+
+// Reward of Bc trajectories whose slot-order masks mask[Bc][W] are already built.
+// `scratch` has at least eval_bytes(); outputs are device pointers (may be null).
+static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, const uint32_t* mask,
+                      int64_t Bc, char* scratch, int64_t scratch_bytes, int sm_count, double n_d,
+                      double res0, double flops0, double alpha, double* reward, double* residual,
+                      int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches) {
+  const int64_t W = P.words();
+  const int64_t Bp = round_up(Bc, 32);
+  const EvalShape s = plan_shape(plan, mode, Bp, sm_count);
+  Carver cv{scratch, scratch + scratch_bytes};
+  uint32_t* maskT = cv.take<uint32_t>(W * Bp);
+  long long* nnz = cv.take<long long>(Bp);
+  double* partial = cv.take<double>((int64_t)s.parts * Bp);
+  double* res2x = cv.take<double>(Bp);
+  int nl = 0;
+
+  if (W > 0) {
+    const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
+    k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+  }
+  k0_popcount_kernel<<<(unsigned)Bc, 256, 0, st>>>(mask, W, Bc, nnz);
+  SPAI_CUDA(cudaGetLastError()); ++nl;
+  if (P.ndup) {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(P.ndup * Bc, 256), 65535);
+    k0_dup_correction_kernel<<<blocks, 256, 0, st>>>(mask, W, Bc, P.dup_start, P.dup_len, P.ndup, nnz);
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+  }
+  if (pt && pt->on) cudaEventRecord(pt->ev[2], st);
+
+  bool use_extra = false;
+  int parts = s.parts;
+  if (mode == SPAI_MODE_COPY) {
+    const dim3 grid(s.gx, s.gy);
+    const size_t smem = (size_t)K3_TILE_C * 16;
+#define SPAI_K3(T, NT)                                                                          \
+  k3_copy_kernel<T, NT><<<grid, K3_THREADS, smem, st>>>(                                        \
+      reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, P.sptr,       \
+      plan.tile_row, plan.ntiles, maskT, Bp, partial)
+    if (plan.ntiles == 0) {
+      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)s.parts * Bp * 8, st));
+    } else if (dtype == SPAI_F32) {
+      if (s.nt == 4) SPAI_K3(float, 4); else if (s.nt == 2) SPAI_K3(float, 2); else SPAI_K3(float, 1);
+    } else {
+      if (s.nt == 4) SPAI_K3(double, 4); else if (s.nt == 2) SPAI_K3(double, 2); else SPAI_K3(double, 1);
+    }
+#undef SPAI_K3
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+  } else {
+    if (!plan.rec_ls) { set_error("plan was built without ls records"); return SPAI_ERR_INVALID; }
+    int off = 0;
+    bool any = false;
+    for (int c = 0; c < LS_NCLASS - 1; ++c) {
+      if (!plan.class_count[c]) continue;
+      double* pp = partial + (int64_t)off * Bp;
+      if (dtype == SPAI_F32) SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, pp, st));
+      else SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, pp, st));
+      off += s.ls_gx[c]; ++nl; any = true;
+    }
+    if (!any) { SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); parts = 1; }
+    else parts = off;
+    if (plan.class_count[LS_GENERIC]) {
+      use_extra = true;
+      SPAI_CUDA(cudaMemsetAsync(res2x, 0, (size_t)Bp * 8, st));
+      const unsigned blocks = (unsigned)(s.generic_warps / 4);
+      if (dtype == SPAI_F32) {
+        float* work = cv.take<float>(s.generic_warps * s.generic_work);
+        int32_t* cmap = cv.take<int32_t>(s.generic_warps * s.generic_cmap);
+        k2_ls_generic_kernel<float><<<blocks, 128, 0, st>>>(
+            reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
+            plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc, work,
+            s.generic_work, cmap, s.generic_cmap, res2x);
+      } else {
+        double* work = cv.take<double>(s.generic_warps * s.generic_work);
+        int32_t* cmap = cv.take<int32_t>(s.generic_warps * s.generic_cmap);
+        k2_ls_generic_kernel<double><<<blocks, 128, 0, st>>>(
+            reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
+            plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc, work,
+            s.generic_work, cmap, s.generic_cmap, res2x);
+      }
+      SPAI_CUDA(cudaGetLastError()); ++nl;
+    }
+  }
+  if (pt && pt->on) cudaEventRecord(pt->ev[3], st);
+  k3_finalize_kernel<<<(unsigned)ceil_div(Bc, 256), 256, 0, st>>>(
+      partial, parts, Bp, Bc, use_extra ? res2x : nullptr, (double)plan.rows_missing_diag, nnz, n_d,
+      res0, flops0, alpha, reward, residual, reinterpret_cast<long long*>(nnz_out));
+  SPAI_CUDA(cudaGetLastError()); ++nl;
+  if (launches) *launches += nl;
+  return SPAI_OK;
+}
+
+}  // namespace spai
+
+// =================================================================== context
+using namespace spai;
+
+struct spai_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int64_t n = 0;
+  Arena arena;            // pattern + CSR
+  Arena plan_arena[2];
+  Pattern P;
+  CsrA A;
+  HostPattern hp;
+  HostCsr ha;
+  Plan plan[2];
+  bool plan_ready[2] = {false, false};
+  bool plan_has_ls[2] = {false, false};
+  double res0[2] = {0, 0};
+  int64_t flops0 = 0;
+  int64_t ws_limit = (int64_t)16 << 30;
+  Workspace ws;
+  PhaseTimer pt;
+  spai_timing last = {};
+};
+
+namespace spai {
+
+static int ensure_plan(spai_ctx* c, int dtype, bool want_ls, cudaStream_t st) {
+  if (c->plan_ready[dtype] && (!want_ls || c->plan_has_ls[dtype])) return SPAI_OK;
+  c->plan_arena[dtype].release();
+  c->plan[dtype] = Plan();
+  // fp32 records always carry `a`; fp64 ls records are a second array
+  SPAI_TRY(build_plan(c->plan_arena[dtype], c->P, c->hp, c->A, c->ha, dtype, want_ls || dtype == SPAI_F32,
+                      c->plan[dtype], st));
+  c->plan_ready[dtype] = true;
+  c->plan_has_ls[dtype] = want_ls || dtype == SPAI_F32;
+  return SPAI_OK;
+}
+
+// ||M A - I||_F with every slot of P kept (B = 1).
+static int residual_all_kept(const Pattern& P, const Plan& plan, int dtype, int sm_count,
+                             double* res_out, cudaStream_t st) {
+  const int64_t W = P.words();
+  Arena tmp;
+  uint32_t* mask = nullptr;
+  SPAI_TRY(tmp.alloc(&mask, W));
+  double* out = nullptr;
+  SPAI_TRY(tmp.alloc(&out, 1));
+  if (W) {
+    k0_mask_init_kernel<<<(unsigned)std::min<int64_t>(ceil_div(W, 256), 65535), 256, 0, st>>>(mask, W, P.E, 1);
+    SPAI_CUDA(cudaGetLastError());
+  }
+  const EvalShape s = plan_shape(plan, SPAI_MODE_COPY, 32, sm_count);
+  const int64_t need = eval_bytes(plan, s, W, 32, dtype);
+  char* scratch = nullptr;
+  SPAI_TRY(tmp.alloc(&scratch, need));
+  SPAI_TRY(eval_masks(P, plan, SPAI_MODE_COPY, dtype, mask, 1, scratch, need, sm_count, (double)P.n, 1.0,
+                      1.0, 0.5, nullptr, out, nullptr, st, nullptr, nullptr));
+  SPAI_CUDA(cudaMemcpyAsync(res_out, out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaStreamSynchronize(st));
+  return SPAI_OK;
+}
+
+static int pair_residual(int sm_count, int64_t n, int64_t m_nnz, const int64_t* mr, const int64_t* mc,
+                         const double* mv, const HostCsr& ha, const CsrA& A, int dtype, double* res,
+                         int64_t* m_nnz_out, cudaStream_t st) {
+  Arena ar;
+  HostPattern hp;
+  Pattern P;
+  SPAI_TRY(build_host_pattern(n, m_nnz, mr, mc, mv, hp, P));
+  // coalesce(): repeated coordinates are summed into one stored entry
+  if (P.ndup) {
+    HostCsr hm;
+    SPAI_TRY(build_host_csr(n, m_nnz, mr, mc, mv, hm));
+    std::vector<int64_t> r2(hm.col.size()), c2(hm.col.size());
+    for (int64_t i = 0; i < n; ++i)
+      for (int32_t p = hm.ptr[i]; p < hm.ptr[i + 1]; ++p) { r2[p] = i; c2[p] = hm.col[p]; }
+    std::vector<double> v2 = hm.val64;
+    if (dtype == SPAI_F32) for (size_t p = 0; p < v2.size(); ++p) v2[p] = hm.val32[p];
+    hp = HostPattern(); P = Pattern();
+    SPAI_TRY(build_host_pattern(n, (int64_t)r2.size(), r2.data(), c2.data(), v2.data(), hp, P));
+  }
+  SPAI_TRY(upload_pattern(ar, hp, P));
+  Plan plan;
+  SPAI_TRY(build_plan(ar, P, hp, A, ha, dtype, false, plan, st));
+  SPAI_TRY(residual_all_kept(P, plan, dtype, sm_count, res, st));
+  if (m_nnz_out) *m_nnz_out = P.init_nnz;
+  return SPAI_OK;
+}
+
+}  // namespace spai
+
+extern "C" {
+
+int spai_abi_version(void) { return SPAI_ABI_VERSION; }
+const char* spai_last_error(void) { return spai::g_err.c_str(); }
+
+int spai_device_count(int* count) {
+  if (!count) return SPAI_ERR_INVALID;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) { *count = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); cudaGetLastError(); return SPAI_ERR_CUDA; }
+  return SPAI_OK;
+}
+
+int spai_ctx_create(int device, int64_t n, int64_t num_edges, const int64_t* edge_row,
+                    const int64_t* edge_col, const double* edge_val, int64_t a_nnz,
+                    const int64_t* a_row, const int64_t* a_col, const double* a_val, spai_ctx** out) {
+  if (!out) return SPAI_ERR_INVALID;
+  *out = nullptr;
+  if (n <= 0 || num_edges < 0 || a_nnz < 0 || n >= ((int64_t)1 << 31) ||
+      (num_edges && (!edge_row || !edge_col || !edge_val)) || (a_nnz && (!a_row || !a_col || !a_val))) {
+    set_error("spai_ctx_create: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  int ndev = 0;
+  SPAI_TRY(spai_device_count(&ndev));
+  if (device < 0 || device >= ndev) { set_error("device %d not available (%d CUDA devices)", device, ndev); return SPAI_ERR_CUDA; }
+  DeviceGuard guard(device);
+  spai_ctx* c = new spai_ctx();
+  c->device = device; c->n = n;
+  auto fail = [&](int s) { delete c; return s; };
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  int s;
+  if ((s = build_host_pattern(n, num_edges, edge_row, edge_col, edge_val, c->hp, c->P))) return fail(s);
+  if ((s = upload_pattern(c->arena, c->hp, c->P))) return fail(s);
+  if ((s = build_host_csr(n, a_nnz, a_row, a_col, a_val, c->ha))) return fail(s);
+  if ((s = upload_csr(c->arena, c->ha, n, a_nnz, c->A))) return fail(s);
+  c->flops0 = 2 * a_nnz * n;                       // preconditioner.py:71-72 on the stored values
+  if ((s = c->pt.init())) return fail(s);
+
+  // baselines ||A0 A0 - I||_F (preconditioner.py:28): pattern = A0 itself
+  {
+    std::vector<int64_t> r(c->ha.col.size()), cc(c->ha.col.size());
+    for (int64_t i = 0; i < n; ++i)
+      for (int32_t p = c->ha.ptr[i]; p < c->ha.ptr[i + 1]; ++p) { r[p] = i; cc[p] = c->ha.col[p]; }
+    for (int dt = 0; dt < 2; ++dt) {
+      std::vector<double> v = c->ha.val64;
+      if (dt == SPAI_F32) for (size_t p = 0; p < v.size(); ++p) v[p] = c->ha.val32[p];
+      if ((s = pair_residual(c->sm_count, n, (int64_t)r.size(), r.data(), cc.data(), v.data(), c->ha, c->A,
+                             dt, &c->res0[dt], nullptr, 0)))
+        return fail(s);
+    }
+  }
+  // the fp32 plan is what the reference-comparable path needs; build it eagerly
+  if ((s = ensure_plan(c, SPAI_F32, false, 0))) return fail(s);
+  *out = c;
+  return SPAI_OK;
+}
+
+void spai_ctx_destroy(spai_ctx* c) {
+  if (!c) return;
+  DeviceGuard guard(c->device);
+  c->pt.destroy();
+  delete c;
+}
+
+int spai_ctx_info(const spai_ctx* c, spai_info* o) {
+  if (!c || !o) return SPAI_ERR_INVALID;
+  memset(o, 0, sizeof(*o));
+  o->n = c->n; o->num_edges = c->P.E; o->init_nnz = c->P.init_nnz; o->num_actions = c->P.init_nnz + 1;
+  o->a_nnz_stored = c->A.nnz_stored; o->a_nnz = c->A.nnz; o->orig_flops = c->flops0;
+  o->orig_residual_f32 = c->res0[SPAI_F32]; o->orig_residual_f64 = c->res0[SPAI_F64];
+  const Plan* p = c->plan_ready[SPAI_F32] ? &c->plan[SPAI_F32] : (c->plan_ready[SPAI_F64] ? &c->plan[SPAI_F64] : nullptr);
+  if (p) {
+    o->contributions = p->nc; o->max_row_union = p->max_q; o->rows_missing_diag = p->rows_missing_diag;
+    for (int i = 0; i < LS_NCLASS; ++i) o->ls_class_rows[i] = p->class_count[i];
+  }
+  o->max_row_slots = c->P.max_k; o->has_duplicates = c->P.ndup ? 1 : 0; o->device = c->device;
+  o->device_bytes = c->arena.bytes + c->plan_arena[0].bytes + c->plan_arena[1].bytes + c->ws.bytes;
+  return SPAI_OK;
+}
+
+int spai_ctx_set_workspace_limit(spai_ctx* c, int64_t bytes) {
+  if (!c || bytes < ((int64_t)1 << 20)) return SPAI_ERR_INVALID;
+  c->ws_limit = bytes;
+  return SPAI_OK;
+}
+
+int spai_ctx_enable_timing(spai_ctx* c, int enable) {
+  if (!c) return SPAI_ERR_INVALID;
+  c->pt.on = enable != 0;
+  return SPAI_OK;
+}
+int spai_ctx_last_timing(const spai_ctx* c, spai_timing* out) {
+  if (!c || !out) return SPAI_ERR_INVALID;
+  *out = c->last;
+  return SPAI_OK;
+}
+
+}  // extern "C"
+
+namespace spai {
+
+enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
+
+// Shared driver of the three reward entry points: chunk the batch so the scratch
+// stays under the workspace limit, build slot-order masks, evaluate.
+static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t B, int64_t T, int64_t ld,
+                         double alpha, int mode, int dtype, double* reward, double* residual,
+                         int64_t* nnz_m, bool out_host, uint8_t* kept_bytes_dev, void* stream) {
+  if (!c || B < 0 || (B && !input) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS) ||
+      (dtype != SPAI_F32 && dtype != SPAI_F64) || (src != FROM_TAKEN_DEV && (T < 0 || ld < T))) {
+    set_error("reward: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  if (B == 0) return SPAI_OK;
+  DeviceGuard guard(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool mask_only = kept_bytes_dev != nullptr;
+  if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode == SPAI_MODE_LS, st));
+  const Plan& plan = c->plan[mask_only ? SPAI_F32 : dtype];
+  const Pattern& P = c->P;
+  const int64_t W = P.words();
+
+  // chunk size
+  const int64_t Bp_all = round_up(B, 32);
+  int64_t Bc = B;
+  auto need_for = [&](int64_t bc) {
+    const int64_t bp = round_up(bc, 32);
+    int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4);                 // mask
+    if (src == FROM_ACTIONS_HOST) need += padded(bc * ld * 8);
+    if (out_host) need += 3 * padded(bp * 8);
+    if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, bp, c->sm_count), W, bp, dtype);
+    return need;
+  };
+  while (Bc > 32 && need_for(Bc) > c->ws_limit) Bc = std::max<int64_t>(32, round_up(Bc / 2, 32));
+  const int64_t need = need_for(Bc);
+  SPAI_TRY(c->ws.ensure(need));
+  (void)Bp_all;
+
+  PhaseTimer* pt = &c->pt;
+  float ms_masks = 0, ms_tr = 0, ms_rw = 0, ms_fin = 0;
+  int launches = 0, chunks = 0;
+  const double res0 = c->res0[dtype];
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t bc = std::min(Bc, B - b0);
+    const int64_t bp = round_up(bc, 32);
+    Carver cv{reinterpret_cast<char*>(c->ws.base), reinterpret_cast<char*>(c->ws.base) + c->ws.bytes};
+    uint32_t* mask = cv.take<uint32_t>(bc * std::max<int64_t>(W, 1));
+    const int64_t* act_dev = nullptr;
+    if (src == FROM_ACTIONS_HOST) {
+      int64_t* buf = cv.take<int64_t>(bc * ld);
+      SPAI_CUDA(cudaMemcpyAsync(buf, reinterpret_cast<const int64_t*>(input) + b0 * ld, (size_t)bc * ld * 8,
+                                cudaMemcpyHostToDevice, st));
+      act_dev = buf;
+    } else if (src == FROM_ACTIONS_DEV) {
+      act_dev = reinterpret_cast<const int64_t*>(input) + b0 * ld;
+    }
+    double* o_rw = nullptr; double* o_rs = nullptr; int64_t* o_nz = nullptr;
+    if (out_host) {
+      o_rw = cv.take<double>(bp); o_rs = cv.take<double>(bp); o_nz = cv.take<int64_t>(bp);
+    } else {
+      o_rw = reward ? reward + b0 : nullptr; o_rs = residual ? residual + b0 : nullptr;
+      o_nz = nnz_m ? nnz_m + b0 : nullptr;
+    }
+    if (pt->on) cudaEventRecord(pt->ev[0], st);
+    if (W > 0) {
+      if (src == FROM_TAKEN_DEV) {
+        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
+        k0_mask_from_taken_kernel<<<blocks, 256, 0, st>>>(
+            reinterpret_cast<const uint32_t*>(input) + b0 * ld, ld, P.identity_perm ? nullptr : P.slot_edge,
+            P.E, mask, W, bc);
+        SPAI_CUDA(cudaGetLastError()); ++launches;
+      } else {
+        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
+        k0_mask_init_kernel<<<blocks, 256, 0, st>>>(mask, W, P.E, bc);
+        SPAI_CUDA(cudaGetLastError()); ++launches;
+        if (T > 0) {
+          constexpr int U = 4;
+          const int64_t chunks_t = ceil_div(T, 256 * U);
+          const int64_t nblk = chunks_t * bc;
+          if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
+          k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
+              act_dev, bc, T, ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t);
+          SPAI_CUDA(cudaGetLastError()); ++launches;
+        }
+      }
+    }
+    if (pt->on) cudaEventRecord(pt->ev[1], st);
+    if (mask_only) {
+      if (P.E > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(P.E * bc, 256), 148 * 32);
+        k0_kept_bytes_kernel<<<blocks, 256, 0, st>>>(mask, W, bc, P.identity_perm ? nullptr : P.edge_slot, P.E,
+                                                    kept_bytes_dev + b0 * P.E);
+        SPAI_CUDA(cudaGetLastError()); ++launches;
+      }
+      ++chunks;
+      continue;
+    }
+    char* scratch = cv.take<char>(0);
+    const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
+    SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
+                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches));
+    if (pt->on) cudaEventRecord(pt->ev[4], st);
+    if (out_host) {
+      if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+      if (residual) SPAI_CUDA(cudaMemcpyAsync(residual + b0, o_rs, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+      if (nnz_m) SPAI_CUDA(cudaMemcpyAsync(nnz_m + b0, o_nz, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+    }
+    ++chunks;
+    if (pt->on) {
+      SPAI_CUDA(cudaEventSynchronize(pt->ev[4]));
+      float t;
+      cudaEventElapsedTime(&t, pt->ev[0], pt->ev[1]); ms_masks += t;
+      cudaEventElapsedTime(&t, pt->ev[1], pt->ev[2]); ms_tr += t;
+      cudaEventElapsedTime(&t, pt->ev[2], pt->ev[3]); ms_rw += t;
+      cudaEventElapsedTime(&t, pt->ev[3], pt->ev[4]); ms_fin += t;
+    }
+    // no sync between chunks: the scratch is reused in stream order
+  }
+  if (out_host) SPAI_CUDA(cudaStreamSynchronize(st));
+  c->last = spai_timing();
+  c->last.ms_masks = ms_masks; c->last.ms_transpose = ms_tr; c->last.ms_reward = ms_rw;
+  c->last.ms_finalize = ms_fin; c->last.ms_total = ms_masks + ms_tr + ms_rw + ms_fin;
+  c->last.launches = launches; c->last.chunks = chunks;
+  c->last.algorithmic_bytes = plan.g_bytes_full;     // per fully-kept pattern; callers scale by nnz_m / E
+  c->last.compulsory_bytes = (double)B * ((double)W * 4.0 + 8.0);
+  return SPAI_OK;
+}
+
+}  // namespace spai
+
+extern "C" {
+
+int spai_reward_batch_host(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
+                           double alpha, int mode, int dtype, double* reward, double* residual,
+                           int64_t* nnz_m, void* stream) {
+  return reward_driver(c, FROM_ACTIONS_HOST, actions, B, T, ld, alpha, mode, dtype, reward, residual, nnz_m,
+                       true, nullptr, stream);
+}
+
+int spai_reward_batch_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
+                          double alpha, int mode, int dtype, double* reward, double* residual,
+                          int64_t* nnz_m, void* stream) {
+  return reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, alpha, mode, dtype, reward, residual, nnz_m,
+                       false, nullptr, stream);
+}
+
+int spai_reward_from_taken_dev(spai_ctx* c, const uint32_t* taken, int64_t B, int64_t words_ld,
+                               double alpha, int mode, int dtype, double* reward, double* residual,
+                               int64_t* nnz_m, void* stream) {
+  if (c && words_ld < c->P.words()) { set_error("taken mask has %lld words per sample, need >= %lld", (long long)words_ld, (long long)c->P.words()); return SPAI_ERR_INVALID; }
+  return reward_driver(c, FROM_TAKEN_DEV, taken, B, 0, words_ld, alpha, mode, dtype, reward, residual, nnz_m,
+                       false, nullptr, stream);
+}
+
+int spai_kept_mask_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
+                       uint8_t* out, void* stream) {
+  if (!out) return SPAI_ERR_INVALID;
+  return reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, 0.5, SPAI_MODE_COPY, SPAI_F32, nullptr, nullptr,
+                       nullptr, false, out, stream);
+}
+
+int spai_row_index_sets(spai_ctx* c, int64_t row, int64_t* num_j, int64_t* j_host, int64_t* num_i,
+                        int64_t* i_host) {
+  if (!c || row < 0 || row >= c->n || !num_j || !num_i) return SPAI_ERR_INVALID;
+  DeviceGuard guard(c->device);
+  SPAI_TRY(ensure_plan(c, SPAI_F32, false, 0));
+  const Plan& plan = c->plan[SPAI_F32];
+  std::vector<int64_t> J;
+  for (int32_t p = c->hp.sptr[row]; p < c->hp.sptr[row + 1]; ++p)
+    if (J.empty() || J.back() != c->hp.slot_col[p]) J.push_back(c->hp.slot_col[p]);
+  const int64_t cb = plan.cptr_host[row], ce = plan.cptr_host[row + 1];
+  std::vector<int32_t> cols(ce - cb);
+  if (ce > cb) SPAI_CUDA(cudaMemcpy(cols.data(), plan.c_col + cb, (ce - cb) * 4, cudaMemcpyDeviceToHost));
+  std::vector<int64_t> I;
+  for (int32_t x : cols) if (I.empty() || I.back() != x) I.push_back(x);
+  for (size_t t = 1; t < cols.size(); ++t)
+    if (cols[t] < cols[t - 1]) { set_error("plan records of row %lld are not sorted", (long long)row); return SPAI_ERR_CUDA; }
+  if (j_host) { if (*num_j < (int64_t)J.size()) return SPAI_ERR_INVALID; std::copy(J.begin(), J.end(), j_host); }
+  if (i_host) { if (*num_i < (int64_t)I.size()) return SPAI_ERR_INVALID; std::copy(I.begin(), I.end(), i_host); }
+  *num_j = (int64_t)J.size();
+  *num_i = (int64_t)I.size();
+  return SPAI_OK;
+}
+
+int spai_ls_solve_values_host(spai_ctx* c, const int64_t* actions, int64_t T, int dtype, double* m_val,
+                              void* stream) {
+  (void)c; (void)actions; (void)T; (void)dtype; (void)m_val; (void)stream;
+  set_error("spai_ls_solve_values_host: not implemented yet");
+  return SPAI_ERR_UNSUPPORTED;
+}
+
+int spai_residual_pair_host(int device, int64_t n, int64_t m_nnz, const int64_t* m_row, const int64_t* m_col,
+                            const double* m_val, int64_t a_nnz, const int64_t* a_row, const int64_t* a_col,
+                            const double* a_val, int dtype, double* residual_out, int64_t* m_nnz_out) {
+  if (n <= 0 || m_nnz < 0 || a_nnz < 0 || !residual_out || (dtype != SPAI_F32 && dtype != SPAI_F64)) {
+    set_error("spai_residual_pair_host: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  int ndev = 0;
+  SPAI_TRY(spai_device_count(&ndev));
+  if (device < 0 || device >= ndev) { set_error("device %d not available", device); return SPAI_ERR_CUDA; }
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  int sm = 148;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sm = prop.multiProcessorCount;
+  Arena ar;
+  HostCsr ha;
+  CsrA A;
+  SPAI_TRY(build_host_csr(n, a_nnz, a_row, a_col, a_val, ha));
+  SPAI_TRY(upload_csr(ar, ha, n, a_nnz, A));
+  return pair_residual(sm, n, m_nnz, m_row, m_col, m_val, ha, A, dtype, residual_out, m_nnz_out, 0);
+}
+
+int spai_sample_step_dev(spai_ctx* c, const float* logits, int64_t logits_ld, int64_t A, uint32_t* taken,
+                         int64_t words_ld, const float* uniforms, uint8_t* done, int64_t B,
+                         int64_t* action, float* prob, void* stream) {
+  if (!c || !logits || !taken || !uniforms || !done || !action || !prob || B < 0 || A <= 0 ||
+      words_ld < (A + 31) / 32 || (logits_ld != 0 && logits_ld < A)) {
+    set_error("spai_sample_step_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  if (B == 0) return SPAI_OK;
+  DeviceGuard guard(c->device);
+  k4_sample_kernel<<<(unsigned)B, K4_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, logits_ld, A, taken, words_ld, uniforms, done, action, prob);
+  SPAI_CUDA(cudaGetLastError());
+  return SPAI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Internal declarations shared by the kernels and the C-ABI host code.
+// sm_100a only. See DESIGN.md for the data layout.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "spai_b200.h"
+
+namespace spai {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+
+#define SPAI_CUDA(call)                                                               \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      ::spai::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+                        cudaGetErrorString(e_));                                      \
+      return SPAI_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+#define SPAI_TRY(call)                 \
+  do {                                 \
+    int s_ = (call);                   \
+    if (s_ != SPAI_OK) return s_;      \
+  } while (0)
+
+// ---------------------------------------------------------------- plan records
+// One record per gathered entry A[c_e, x] of row i ("contribution"): slot e of
+// the row's candidate list reaches output column x. Records of a row are sorted
+// by (x, e); records with the same x form one output segment (one entry of the
+// row of M*A). 16 bytes, so a run of records is a legal cp.async.bulk source.
+//   flags: bit0 END  last record of its output segment
+//          bit1 DIAG the segment's column is the row index (the "-I" entry)
+//          bits 2..15  e  slot index inside the row (< 16384)
+//          bits 16..31 s  output segment index inside the row (< 65536)
+constexpr uint32_t F_END = 1u;
+constexpr uint32_t F_DIAG = 2u;
+constexpr int MAX_ROW_SLOTS = 16384;
+constexpr int MAX_ROW_UNION = 65536;
+
+__host__ __device__ __forceinline__ uint32_t rec_e(uint32_t flags) { return (flags >> 2) & 0x3fffu; }
+__host__ __device__ __forceinline__ uint32_t rec_s(uint32_t flags) { return flags >> 16; }
+
+struct alignas(16) Rec32 {
+  uint32_t ebit;   // 1u << e when the row has <= 32 slots, else 0
+  uint32_t flags;
+  float w;         // fl32(m_e * a): copy mode adds this when slot e is kept
+  float a;         // A[c_e, x]: ls mode tile entry
+};
+struct alignas(16) Rec64 {
+  uint32_t ebit;
+  uint32_t flags;
+  double v;        // w (copy plan) or a (ls plan)
+};
+template <typename T> struct RecOf;
+template <> struct RecOf<float> { using type = Rec32; };
+template <> struct RecOf<double> { using type = Rec64; };
+
+__device__ __forceinline__ float rec_w(const Rec32& r) { return r.w; }
+__device__ __forceinline__ double rec_w(const Rec64& r) { return r.v; }
+__device__ __forceinline__ float rec_a(const Rec32& r) { return r.a; }
+__device__ __forceinline__ double rec_a(const Rec64& r) { return r.v; }
+
+// ---------------------------------------------------------------- device data
+struct Pattern {            // initial matrix: candidate superset S in slot order
+  int64_t n = 0, E = 0;
+  int32_t* sptr = nullptr;        // [n+1] slot offsets; slots sorted by (row, col, edge id)
+  int32_t* slot_col = nullptr;    // [E]
+  int32_t* slot_edge = nullptr;   // [E] slot -> edge id (caller order)
+  int32_t* edge_slot = nullptr;   // [E] edge id -> slot
+  float* slot_val32 = nullptr;    // [E]
+  double* slot_val64 = nullptr;   // [E]
+  int32_t* dup_start = nullptr;   // [ndup] first slot of every coordinate group with > 1 slot
+  int32_t* dup_len = nullptr;     // [ndup]
+  int64_t ndup = 0;
+  int64_t init_nnz = 0;           // distinct coordinates
+  int max_k = 0;
+  bool identity_perm = false;
+  int64_t words() const { return (E + 31) / 32; }
+};
+
+struct CsrA {               // original matrix, coalesced
+  int64_t n = 0, nnz = 0, nnz_stored = 0;
+  int32_t* ptr = nullptr;   // [n+1]
+  int32_t* col = nullptr;   // [nnz]
+  float* val32 = nullptr;
+  double* val64 = nullptr;
+};
+
+constexpr int LS_NCLASS = 8;     // last class = generic fallback
+constexpr int LS_GENERIC = LS_NCLASS - 1;
+
+struct Plan {
+  int dtype = -1;
+  int64_t n = 0;
+  int64_t nc = 0;                 // total contributions
+  int64_t* cptr = nullptr;        // [n+1] device
+  std::vector<int64_t> cptr_host;
+  int32_t* c_col = nullptr;       // [nc] output column of every record
+  void* rec_copy = nullptr;       // Rec32 / Rec64(w)
+  void* rec_ls = nullptr;         // Rec32 (same array) / Rec64(a)
+  int32_t* r_q = nullptr;         // [n] |I_i|
+  int32_t* r_diag = nullptr;      // [n] segment index of column i, or -1
+  int64_t rows_missing_diag = 0;  // rows with r_diag < 0 (each adds 1 to ||.||^2)
+  int max_q = 0;
+  // copy-kernel tiling: tile t = rows [tile_row[t], tile_row[t+1])
+  int32_t* tile_row = nullptr;    // [ntiles+1] device
+  int ntiles = 0;
+  // ls-kernel row classes
+  int32_t* class_rows[LS_NCLASS] = {};
+  int64_t class_count[LS_NCLASS] = {};
+  int64_t generic_max_q = 0, generic_max_k = 0;
+  double g_bytes_full = 0;        // SURVEY §8d G with every candidate kept (bytes / pattern)
+  int64_t bytes = 0;
+};
+
+// ---------------------------------------------------------------- small helpers
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+}  // namespace spai

@@ -1,0 +1,175 @@
+/*
+ * spai_b200.h — C ABI of the B200-native SPAI reward path (libspai_b200.so).
+ *
+ * The reference (tonylizza/gflownet-spai) is pure Python and has no FFI; its
+ * seam is the Python `Env` protocol. Each entry point below cites the reference
+ * interface it replaces (file:line relative to the reference checkout). The
+ * host-side mirror of that protocol is gflownet_spai_b200/env.py; the ctypes
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross the boundary;
+ *   - every function returns an int status (SPAI_OK == 0); no exceptions;
+ *     spai_last_error() returns a thread-local message for the last failure;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - pointers named *_dev are device pointers on the context's device,
+ *     *_host are host pointers (pinned host memory makes copies asynchronous);
+ *   - calls enqueue on `stream`; only functions that fill HOST outputs
+ *     synchronise that stream before returning.
+ */
+#ifndef SPAI_B200_H_
+#define SPAI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPAI_ABI_VERSION 1
+
+enum spai_status {
+  SPAI_OK = 0,
+  SPAI_ERR_INVALID = 1,      /* bad argument (the reference raises ValueError) */
+  SPAI_ERR_CUDA = 2,         /* CUDA runtime error, see spai_last_error()      */
+  SPAI_ERR_UNSUPPORTED = 3,  /* shape outside the supported envelope           */
+  SPAI_ERR_NOMEM = 4
+};
+
+enum spai_mode {
+  SPAI_MODE_COPY = 0, /* surviving entries keep their values: what the reference
+                         computes (gflownet/utils.py:331-337)                  */
+  SPAI_MODE_LS = 1    /* re-solve every row's least-squares problem on its
+                         pattern (BASELINE.json north star; no reference code) */
+};
+
+enum spai_dtype { SPAI_F32 = 0, SPAI_F64 = 1 };
+
+typedef struct spai_ctx spai_ctx; /* opaque */
+
+typedef struct spai_info {
+  int64_t n;             /* matrix size                       preconditioner.py:13 */
+  int64_t num_edges;     /* E: entries of the initial matrix in caller order (:23) */
+  int64_t init_nnz;      /* distinct coordinates (coalesced count)           (:14) */
+  int64_t num_actions;   /* init_nnz + 1                                     (:16) */
+  int64_t a_nnz_stored;  /* stored values of the original matrix             (:71) */
+  int64_t a_nnz;         /* coalesced nnz of the original matrix                   */
+  int64_t orig_flops;    /* 2 * a_nnz_stored * n                          (:29,:72) */
+  double orig_residual_f32; /* ||A0 A0 - I||_F, fp32 products (reference)    (:28) */
+  double orig_residual_f64; /* same, fp64 products                                 */
+  int64_t contributions; /* sum over rows of gathered A entries (plan size)        */
+  int32_t max_row_slots; /* max candidates per row (k)                             */
+  int32_t max_row_union; /* max |I_i| (q)                                          */
+  int32_t has_duplicates;/* initial matrix has repeated coordinates                */
+  int32_t device;
+  int64_t rows_missing_diag; /* rows whose union index set misses the diagonal     */
+  int64_t ls_class_rows[8];  /* rows per ls kernel class (last = generic)          */
+  int64_t device_bytes;      /* bytes of device memory held by the context         */
+} spai_info;
+
+int spai_abi_version(void);
+const char* spai_last_error(void);
+int spai_device_count(int* count);
+
+/* PreconditionerEnv.__init__ (preconditioner.py:12-29): captures the edge table
+ * in the caller's COO order (action k == k-th entry as given, explicit zeros and
+ * repeated coordinates included), coalesces the original matrix to CSR, builds
+ * the per-row gather plans on the device (kernel K1) and the baseline constants
+ * res0 = ||A0 A0 - I||_F and flops0. All inputs are HOST arrays; values are fp64
+ * and are rounded to fp32 for the fp32 path exactly as the reference's
+ * `.float()` does (preconditioner.py:25). */
+int spai_ctx_create(int device, int64_t n,
+                    int64_t num_edges, const int64_t* edge_row_host,
+                    const int64_t* edge_col_host, const double* edge_val_host,
+                    int64_t a_nnz, const int64_t* a_row_host, const int64_t* a_col_host,
+                    const double* a_val_host, spai_ctx** out);
+void spai_ctx_destroy(spai_ctx* ctx);
+int spai_ctx_info(const spai_ctx* ctx, spai_info* out);
+
+/* Cap on the scratch memory (masks + partial sums) one reward call may use;
+ * larger batches are processed in trajectory chunks. Default 16 GiB. */
+int spai_ctx_set_workspace_limit(spai_ctx* ctx, int64_t bytes);
+
+/* PreconditionerEnv.update (preconditioner.py:32-52) for a whole batch:
+ * actions int64[B, T] with leading dimension `ld` (>= T), -1 padded; ids outside
+ * [0, E) — the terminal id included — match no edge (gflownet/utils.py:323).
+ * Outputs (each may be NULL): reward f64[B] (preconditioner.py:64), residual
+ * f64[B] (:90), nnz_m i64[B] (:71).
+ *   reward = 1000 * (alpha*(1 - res/res0) + (1-alpha)*(1 - flops/flops0)).
+ * `res0` is the fp32-product baseline for SPAI_F32 and the fp64 one for SPAI_F64.
+ * *_host variant: host in / host out, copies on `stream`, synchronises it. */
+int spai_reward_batch_host(spai_ctx* ctx, const int64_t* actions_host, int64_t B, int64_t T,
+                           int64_t ld, double alpha, int mode, int dtype,
+                           double* reward_host, double* residual_host, int64_t* nnz_m_host,
+                           void* stream);
+int spai_reward_batch_dev(spai_ctx* ctx, const int64_t* actions_dev, int64_t B, int64_t T,
+                          int64_t ld, double alpha, int mode, int dtype,
+                          double* reward_dev, double* residual_dev, int64_t* nnz_m_dev,
+                          void* stream);
+
+/* gflownet/utils.py:315-323 on its own: kept-edge mask of every trajectory in
+ * EDGE (caller) order, one byte per edge: out_dev u8[B, E]. The bit-exact
+ * artefact compared with the reference's `remaining_edges_mask`. */
+int spai_kept_mask_dev(spai_ctx* ctx, const int64_t* actions_dev, int64_t B, int64_t T,
+                       int64_t ld, uint8_t* out_dev, void* stream);
+
+/* Reward from an already-built "taken" bitmask in EDGE order (the sampler's
+ * state, bit e of word e/32 set == edge e removed): taken_dev u32[B, words],
+ * words = ceil(num_actions / 32). Skips the actions->mask step. */
+int spai_reward_from_taken_dev(spai_ctx* ctx, const uint32_t* taken_dev, int64_t B,
+                               int64_t words_ld, double alpha, int mode, int dtype,
+                               double* reward_dev, double* residual_dev, int64_t* nnz_m_dev,
+                               void* stream);
+
+/* Gathered index sets of the plan, for parity tests: for row i,
+ * J_i = candidate columns (sorted), I_i = union of cols(A[c,:]), c in J_i
+ * (sorted). Two-call protocol: pass NULL arrays to get the counts. HOST out. */
+int spai_row_index_sets(spai_ctx* ctx, int64_t row, int64_t* num_j, int64_t* j_host,
+                        int64_t* num_i, int64_t* i_host);
+
+/* ls mode: values of M re-solved on the pattern of ONE trajectory, in EDGE
+ * order (0 for removed edges): m_val_host f64[E]. */
+int spai_ls_solve_values_host(spai_ctx* ctx, const int64_t* actions_host, int64_t T,
+                              int dtype, double* m_val_host, void* stream);
+
+/* PreconditionerEnv.calculate_residual (preconditioner.py:79-93) for an
+ * arbitrary pair of sparse matrices given as HOST COO: ||M @ A - I||_F on the
+ * device; also returns the stored-entry count of M after coalescing. */
+int spai_residual_pair_host(int device, int64_t n, int64_t m_nnz, const int64_t* m_row_host,
+                            const int64_t* m_col_host, const double* m_val_host, int64_t a_nnz,
+                            const int64_t* a_row_host, const int64_t* a_col_host,
+                            const double* a_val_host, int dtype, double* residual_out,
+                            int64_t* m_coalesced_nnz_out);
+
+/* One masked-categorical environment step (policy.py:64-73, gflownet.py:116-119,
+ * :148, :177-179, log.py:67-87) for B samples:
+ *   logits_dev f32[A] (logits_ld == 0: one vector shared by all samples) or
+ *   f32[B, A] with leading dimension logits_ld; taken_dev u32[B, words_ld] is
+ *   read and, for the sampled id, updated in place; uniforms_dev f32[B] in
+ *   [0,1) drive the inverse-CDF draw; done_dev u8[B] in/out (set when the
+ *   terminal id A-1 is drawn); action_dev i64[B] (-1 for finished samples);
+ *   prob_dev f32[B] (1.0 for finished samples) = masked softmax probability of
+ *   the drawn id. A = number of actions (length of a logits row; the terminal
+ *   id is A-1, gflownet.py:177). */
+int spai_sample_step_dev(spai_ctx* ctx, const float* logits_dev, int64_t logits_ld, int64_t A,
+                         uint32_t* taken_dev, int64_t words_ld, const float* uniforms_dev,
+                         uint8_t* done_dev, int64_t B, int64_t* action_dev, float* prob_dev,
+                         void* stream);
+
+/* Per-kernel device time of the LAST reward call on this context, in ms,
+ * measured with CUDA events on the caller's stream (masks, transpose, reward
+ * kernel, finalize) and the number of kernels launched by it. */
+typedef struct spai_timing {
+  float ms_masks, ms_transpose, ms_reward, ms_finalize, ms_total;
+  int32_t launches;
+  int32_t chunks;
+  double algorithmic_bytes; /* SURVEY.md §8d G summed over the batch            */
+  double compulsory_bytes;  /* bytes that must cross HBM for the batch           */
+} spai_timing;
+int spai_ctx_enable_timing(spai_ctx* ctx, int enable);
+int spai_ctx_last_timing(const spai_ctx* ctx, spai_timing* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPAI_B200_H_ */

@@ -1,0 +1,236 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+reference's golden outputs and the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north star): masks / index sets bit-exact; fp64 reward
+1e-10 relative; fp32 reward 1e-4 relative (atol covers rewards that are ~0 on a
+scale of 1000)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from gflownet_spai_b200 import synth
+from oracle import spai_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL32, ATOL32 = 1e-4, 2e-2
+RTOL64, ATOL64 = 1e-10, 1e-8
+
+
+def _ctx_from_golden(g):
+    from gflownet_spai_b200.env import SpaiContext
+    return SpaiContext(int(g["n"]), g["edge_row"], g["edge_col"], g["edge_val"].astype(np.float64),
+                       g["a_row"], g["a_col"], g["a_val"].astype(np.float64), device=0)
+
+
+def _a_csr(g, dtype):
+    n = int(g["n"])
+    a = sp.coo_matrix((g["a_val"].astype(dtype), (g["a_row"], g["a_col"])), shape=(n, n)).tocsr()
+    a.sum_duplicates()
+    a.sort_indices()
+    return a
+
+
+def test_copy_fp32_matches_reference_golden(golden):
+    g = golden
+    ctx = _ctx_from_golden(g)
+    info = ctx.info()
+    assert info.init_nnz == int(g["init_nnz"])
+    assert info.num_actions == int(g["num_actions"])
+    assert info.orig_flops == int(g["orig_flops"])
+    assert info.orig_residual_f32 == pytest.approx(float(g["orig_residual"]), rel=1e-6)
+    acts = torch.from_numpy(g["actions"])
+    for a_in in (acts, acts.cuda()):
+        out = ctx.reward_batch(a_in, float(g["alpha"]), "copy", torch.float32)
+        np.testing.assert_allclose(out["reward"].cpu().numpy(), g["reward"], rtol=RTOL32, atol=ATOL32)
+    ctx.close()
+
+
+def test_kept_masks_and_pattern_indices_bit_exact(golden):
+    g = golden
+    ctx = _ctx_from_golden(g)
+    n = int(g["n"])
+    kept = ctx.kept_mask(torch.from_numpy(g["actions"])).cpu().numpy().astype(bool)
+    nnz = ctx.reward_batch(torch.from_numpy(g["actions"]).cuda(), 0.5)["nnz_m"].cpu().numpy()
+    for b in range(kept.shape[0]):
+        assert np.array_equal(kept[b], orc.kept_edge_mask(g["edge_row"].size, g["actions"][b]))
+        # coalesced (row, col) of M implied by the mask == the reference's resize_sparse_tensor output
+        key = np.unique(g["edge_row"][kept[b]] * n + g["edge_col"][kept[b]])
+        lo, hi = int(g["m_ptr"][b]), int(g["m_ptr"][b + 1])
+        assert np.array_equal(key // n, g["m_row"][lo:hi])
+        assert np.array_equal(key % n, g["m_col"][lo:hi])
+        assert nnz[b] == hi - lo
+    ctx.close()
+
+
+def test_copy_fp64_matches_oracle(golden):
+    g = golden
+    ctx = _ctx_from_golden(g)
+    n = int(g["n"])
+    want = orc.reward_batch_copy(n, g["edge_row"], g["edge_col"], g["edge_val"].astype(np.float64),
+                                 _a_csr(g, np.float64), g["actions"], float(g["alpha"]), dtype=np.float64,
+                                 a_stored_nnz=g["a_val"].size)
+    out = ctx.reward_batch(torch.from_numpy(g["actions"]).cuda(), float(g["alpha"]), "copy", torch.float64)
+    np.testing.assert_allclose(out["residual"].cpu().numpy(), want["residual"], rtol=RTOL64, atol=ATOL64)
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), want["reward"], rtol=RTOL64, atol=ATOL64)
+    assert np.array_equal(out["nnz_m"].cpu().numpy(), want["nnz_m"])
+    assert ctx.info().orig_residual_f64 == pytest.approx(want["orig_residual"], rel=1e-12)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["poisson10", "convdiff16", "uncoalesced40", "tiny3"])
+def test_ls_matches_oracle(name):
+    import conftest
+    g = conftest.load_golden(name)
+    ctx = _ctx_from_golden(g)
+    n = int(g["n"])
+    a64 = _a_csr(g, np.float64)
+    acts = g["actions"][:6]
+    want = orc.reward_batch_ls(n, g["edge_row"], g["edge_col"], a64, acts, float(g["alpha"]), dtype=np.float64,
+                               a_stored_nnz=g["a_val"].size, baseline_dtype=np.float64)
+    out = ctx.reward_batch(torch.from_numpy(acts).cuda(), float(g["alpha"]), "ls", torch.float64)
+    np.testing.assert_allclose(out["residual"].cpu().numpy(), want["residual"], rtol=RTOL64, atol=ATOL64)
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), want["reward"], rtol=RTOL64, atol=1e-7)
+    want32 = orc.reward_batch_ls(n, g["edge_row"], g["edge_col"], a64, acts, float(g["alpha"]), dtype=np.float32,
+                                 a_stored_nnz=g["a_val"].size, baseline_dtype=np.float32)
+    out32 = ctx.reward_batch(torch.from_numpy(acts).cuda(), float(g["alpha"]), "ls", torch.float32)
+    np.testing.assert_allclose(out32["reward"].cpu().numpy(), want32["reward"], rtol=RTOL32, atol=ATOL32)
+    # LS optimality: never worse than keeping the values
+    cp = ctx.reward_batch(torch.from_numpy(acts).cuda(), float(g["alpha"]), "copy", torch.float64)
+    assert torch.all(out["residual"] <= cp["residual"] + 1e-9)
+    ctx.close()
+
+
+def test_gathered_index_sets_bit_exact():
+    a = synth.convdiff2d(12)
+    n = a.shape[0]
+    r, c = synth.superset_pattern(a, 8, max_power=2)
+    v = synth.neumann_values(a, r, c)
+    coo = a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(n, r, c, v, coo.row, coo.col, coo.data)
+    pat = sp.csr_matrix((np.ones(r.size), (r, c)), shape=(n, n))
+    for i in list(range(0, n, 7)) + [n - 1]:
+        j, iset = ctx.row_index_sets(i)
+        wj, wi = orc.row_index_sets(pat, a, i)
+        assert np.array_equal(j, wj) and np.array_equal(iset, wi)
+    info = ctx.info()
+    assert info.max_row_slots == 8
+    ctx.close()
+
+
+def _random_problem(n, row_nnz, a_row_nnz, seed):
+    rng = np.random.default_rng(seed)
+    a = sp.random(n, n, density=a_row_nnz / n, random_state=seed, format="csr") + sp.identity(n) * 3.0
+    a = sp.csr_matrix(a)
+    a.sort_indices()
+    rows, cols = [], []
+    for i in range(n):
+        k = int(rng.integers(0, row_nnz + 1))
+        cc = rng.choice(n, size=min(k, n), replace=False)
+        rows.append(np.full(cc.size, i))
+        cols.append(cc)
+    r = np.concatenate(rows).astype(np.int64)
+    c = np.concatenate(cols).astype(np.int64)
+    perm = rng.permutation(r.size)
+    r, c = r[perm], c[perm]
+    v = rng.uniform(-1, 1, r.size)
+    return a, r, c, v
+
+
+@pytest.mark.parametrize("row_nnz,a_row_nnz", [(48, 6), (20, 30), (6, 3)])
+def test_wide_rows_and_generic_ls_fallback(row_nnz, a_row_nnz):
+    """Rows with > 32 candidates (wide copy path) and union sets beyond the
+    register kernels' classes (generic ls kernel); empty rows included."""
+    n = 96
+    a, r, c, v = _random_problem(n, row_nnz, a_row_nnz, seed=row_nnz)
+    coo = a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(n, r, c, v, coo.row, coo.col, coo.data)
+    acts = synth.make_trajectories(r.size, 5, seed0=9)
+    t = torch.from_numpy(acts).cuda()
+    want = orc.reward_batch_copy(n, r, c, v, a, acts, 0.5, dtype=np.float64)
+    got = ctx.reward_batch(t, 0.5, "copy", torch.float64)
+    np.testing.assert_allclose(got["residual"].cpu().numpy(), want["residual"], rtol=RTOL64, atol=ATOL64)
+    assert np.array_equal(got["nnz_m"].cpu().numpy(), want["nnz_m"])
+    want32 = orc.reward_batch_copy(n, r, c, v.astype(np.float32), a.astype(np.float32), acts, 0.5, dtype=np.float32)
+    got32 = ctx.reward_batch(t, 0.5, "copy", torch.float32)
+    np.testing.assert_allclose(got32["reward"].cpu().numpy(), want32["reward"], rtol=RTOL32, atol=ATOL32)
+    wls = orc.reward_batch_ls(n, r, c, a, acts, 0.5, dtype=np.float64, baseline_dtype=np.float64)
+    gls = ctx.reward_batch(t, 0.5, "ls", torch.float64)
+    np.testing.assert_allclose(gls["residual"].cpu().numpy(), wls["residual"], rtol=1e-9, atol=1e-8)
+    ctx.close()
+
+
+def test_taken_bitmask_entry_point_equals_action_entry_point():
+    p = synth.make_problem("cfg2", scale=0.125)          # 32 x 32 grid
+    coo = p.a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data)
+    acts = synth.make_trajectories(p.num_edges, 40, seed0=1)
+    e = p.num_edges
+    words = (e + 1 + 31) // 32
+    taken = np.zeros((acts.shape[0], words), dtype=np.uint32)
+    for b in range(acts.shape[0]):
+        ids = acts[b][(acts[b] >= 0) & (acts[b] < e)]
+        np.bitwise_or.at(taken[b], ids // 32, (np.uint32(1) << (ids % 32).astype(np.uint32)))
+    t_taken = torch.from_numpy(taken.view(np.int32)).cuda()
+    one = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.25, "copy", torch.float64)
+    two = ctx.reward_from_taken(t_taken, 0.25, "copy", torch.float64)
+    assert torch.equal(one["nnz_m"], two["nnz_m"])
+    assert torch.allclose(one["reward"], two["reward"], rtol=1e-13, atol=1e-10)
+    ctx.close()
+
+
+def test_chunked_batches_match_single_pass_and_edge_cases():
+    p = synth.make_problem("cfg2", scale=0.0625)         # 16 x 16 grid
+    coo = p.a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data)
+    acts = synth.make_trajectories(p.num_edges, 300, seed0=3)
+    full = ctx.reward_batch(torch.from_numpy(acts), 0.5, "copy", torch.float32)
+    ctx.set_workspace_limit(1 << 20)                     # forces several trajectory chunks
+    chunked = ctx.reward_batch(torch.from_numpy(acts), 0.5, "copy", torch.float32)
+    assert torch.allclose(full["reward"], chunked["reward"], rtol=1e-12, atol=1e-9)
+    # empty batch / zero-length trajectories / single trajectory
+    empty = ctx.reward_batch(torch.zeros((0, 4), dtype=torch.int64), 0.5)
+    assert empty["reward"].numel() == 0
+    none = ctx.reward_batch(torch.zeros((3, 0), dtype=torch.int64).cuda(), 0.5, "copy", torch.float64)
+    allkept = ctx.reward_batch(torch.full((1, 2), -1, dtype=torch.int64).cuda(), 0.5, "copy", torch.float64)
+    assert torch.allclose(none["reward"], allkept["reward"].expand(3))
+    assert int(allkept["nnz_m"][0]) == p.num_edges
+    with pytest.raises(ValueError):
+        ctx.reward_batch(torch.zeros((2, 2), dtype=torch.int32), 0.5)
+    ctx.close()
+
+
+def test_drop_in_env_matches_reference_outputs(golden):
+    """The PreconditionerEnv mirror: constructor attributes, update(), reward(),
+    calculate_residual() read like the reference's (preconditioner.py)."""
+    from gflownet_spai_b200.env import PreconditionerEnv
+    g = golden
+    n = int(g["n"])
+    init = torch.sparse_coo_tensor(torch.tensor(np.stack([g["edge_row"], g["edge_col"]])),
+                                   torch.tensor(g["edge_val"]), (n, n))
+    orig = torch.sparse_coo_tensor(torch.tensor(np.stack([g["a_row"], g["a_col"]])),
+                                   torch.tensor(g["a_val"]), (n, n))
+    env = PreconditionerEnv(n, init, orig)
+    assert env.init_nnz == int(g["init_nnz"]) and env.num_actions == int(g["num_actions"])
+    assert env.state_dim == env.init_nnz and env.orig_flops == int(g["orig_flops"])
+    assert float(env.orig_residual) == pytest.approx(float(g["orig_residual"]), rel=1e-6)
+    assert env.data.edge_index.shape == (2, g["edge_row"].size) and "edge_attr" in env.data
+    rewards = env.update([init] * g["actions"].shape[0], torch.from_numpy(g["actions"]), torch.tensor(float(g["alpha"])))
+    assert isinstance(rewards, list) and rewards[0].dtype == torch.float64 and rewards[0].dim() == 0
+    got = torch.tensor(rewards, dtype=torch.float32).numpy()
+    np.testing.assert_allclose(got, g["reward"].astype(np.float32), rtol=RTOL32, atol=ATOL32)
+    # reward(s, ...) on an explicit matrix == update() on the trajectory that produces it
+    b = 0
+    kept = orc.kept_edge_mask(g["edge_row"].size, g["actions"][b])
+    s = torch.sparse_coo_tensor(torch.tensor(np.stack([g["edge_row"][kept], g["edge_col"][kept]])),
+                                torch.tensor(g["edge_val"][kept]), (n, n)).coalesce()
+    r1 = env.reward(s, int(kept.sum()), float(g["alpha"]))
+    assert float(r1) == pytest.approx(float(g["reward"][b]), rel=RTOL32, abs=ATOL32)
+    assert env.mask([0, 1]).shape == (2, env.num_actions)
+    with pytest.raises(ValueError):
+        env.create_mask_from_sparse_matrix(torch.eye(3))
