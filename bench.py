@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""Benchmark of the SPAI reward hot path (BASELINE.json metric: candidate
+patterns scored / s, row least-squares solves / s, % of the HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU port of the reference
+
+One "step" scores one batch of B sampled patterns (trajectories) of the named
+config. Default workload (N=1): cfg2 = 2-D 5-point Poisson 256x256
+(n=65 536), candidate superset <= 8 per row (E = 524 280), B = 4096
+trajectories per GPU, copy mode / fp32 — the semantics and precision of the
+reference's own `PreconditionerEnv.update` (the reference arm computes exactly
+this). `--mode ls` switches the headline to the north-star least-squares
+re-solve, which the reference cannot run.
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spai_patterns_scored_per_s"
+UNIT = "patterns/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the grid (testing only)")
+    ap.add_argument("--mode", default="copy", choices=["copy", "ls"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (0 = config default)")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="trajectories in the CPU-baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ls-mode side measurements")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args, p, batch):
+    desc = {"cfg1": "2-D Poisson 10x10", "cfg2": "2-D 5-pt Poisson 256x256", "cfg3": "3-D 7-pt Poisson 64^3",
+            "cfg4": "2-D convection-diffusion 512x512", "cfg5": "banded+power-law n=1M"}[args.config]
+    return (f"{args.config}: {desc} n={p.n} E={p.num_edges} (<= {p.k}/row), B={batch}/GPU, "
+            f"{args.mode}/{args.dtype}")
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# synthetic trajectories on the device (seeded per global trajectory index)
+# ---------------------------------------------------------------------------
+def device_trajectories(num_edges, batch, first, device):
+    import torch
+    lens = []
+    gens = []
+    for b in range(batch):
+        g = torch.Generator(device=device)
+        g.manual_seed(1000 + first + b)
+        u = float(torch.rand(1, generator=g, device=device))
+        lens.append(int(np.floor(u * num_edges * 0.5)))
+        gens.append(g)
+    tmax = max(lens) + 1
+    acts = torch.full((batch, tmax), -1, dtype=torch.int64, device=device)
+    for b in range(batch):
+        t = lens[b]
+        if t:
+            acts[b, :t] = torch.randperm(num_edges, generator=gens[b], device=device)[:t]
+        acts[b, t] = num_edges
+    return acts
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------
+# CPU arms (oracle port of the reference; bench.py may execute oracle/ only here)
+# ---------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(cfg, scale):
+    from gflownet_spai_b200 import synth
+    p = synth.make_problem(cfg, scale)
+    _W["p"] = p
+    _W["a32"] = p.a.astype(np.float32)
+    _W["v32"] = p.edge_val.astype(np.float32)
+
+
+def _cpu_worker(args):
+    from gflownet_spai_b200 import synth
+    from oracle import spai_oracle as orc
+    first, count = args
+    p = _W["p"]
+    acts = synth.make_trajectories(p.num_edges, count, first=first)
+    res0, flops0 = _W.get("base") or orc.baseline_constants(_W["a32"], None, np.float32)
+    _W["base"] = (res0, flops0)
+    t0 = time.perf_counter()
+    out = []
+    for b in range(count):
+        kept = orc.kept_edge_mask(p.num_edges, acts[b])
+        m = orc.build_pattern_matrix(p.n, p.edge_row, p.edge_col, _W["v32"], kept, dtype=np.float32)
+        res = orc.residual_copy(m, _W["a32"], dtype=np.float32)
+        out.append(orc.reward_from_residual(res, m.nnz, p.n, res0, flops0, 0.5))
+    return time.perf_counter() - t0, out
+
+
+def cpu_port_throughput(cfg, scale, sample, procs):
+    """patterns/s of the numpy/scipy restatement of PreconditionerEnv.update
+    (preconditioner.py:32-52, copy mode, fp32) on `procs` host processes."""
+    import multiprocessing as mp
+    if procs <= 1:
+        _cpu_worker_init(cfg, scale)
+        _cpu_worker((0, 1))                      # baseline constants + warm caches
+        dt, _ = _cpu_worker((0, sample))
+        return sample / dt, dt
+    ctx = mp.get_context("fork")
+    per = max(1, sample // procs)
+    with ctx.Pool(procs, initializer=_cpu_worker_init, initargs=(cfg, scale)) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * procs)  # warm every worker
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i * per, per) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return per * procs / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    from gflownet_spai_b200 import synth
+    p = synth.make_problem(args.config, args.scale)
+    batch = args.batch or p.batch
+    per_step = max(procs, min(args.cpu_sample, 4 * procs))
+    vals = []
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    per = max(1, per_step // procs)
+    with ctx.Pool(procs, initializer=_cpu_worker_init, initargs=(args.config, args.scale)) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_worker, [(i * per, per) for i in range(procs)])
+        t_all = time.perf_counter()
+        for s in range(args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [((s * procs + i) * per, per) for i in range(procs)])
+            vals.append(time.perf_counter() - t0)
+        total = time.perf_counter() - t_all
+    value = per * procs * args.steps / total
+    sample = (f"each step = {per * procs} trajectories of the workload (of B={batch}) over {procs} processes; "
+              "numpy/scipy restatement of the reference's update() (no gc.collect, no Python set loop)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": {"workload": workload_name(args, p, batch)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def algorithmic_bytes(ctx, p, acts_dev, mode, wbytes):
+    """SURVEY.md §8d gather-inclusive G summed over the batch, from the inputs
+    alone: for every kept candidate (i, c): 4 (pattern col id) + w (M value, copy
+    mode) + 2*4 (rowptr of A[c,:]) + nnz(A[c,:]) * (4 + w); + 8 per pattern."""
+    import torch
+    rlen = np.diff(p.a.indptr)[p.edge_col].astype(np.float64)
+    cost = 4.0 + (wbytes if mode == "copy" else 0.0) + 8.0 + rlen * (4.0 + wbytes)
+    cost_t = torch.from_numpy(cost).to(acts_dev.device)
+    total = 0.0
+    for b0 in range(0, acts_dev.shape[0], 256):
+        kept = ctx.kept_mask(acts_dev[b0:b0 + 256])
+        total += float((kept.to(torch.float64) @ cost_t).sum())
+        del kept
+    return total + 8.0 * acts_dev.shape[0]
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from gflownet_spai_b200 import synth
+    from gflownet_spai_b200.env import SpaiContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdtype = torch.float32 if args.dtype == "f32" else torch.float64
+    wbytes = 4.0 if args.dtype == "f32" else 8.0
+
+    p = synth.make_problem(args.config, args.scale)
+    batch = args.batch or p.batch
+    coo = p.a.tocoo()
+    t0 = time.perf_counter()
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, device=local)
+    setup_s = time.perf_counter() - t0
+    acts = device_trajectories(p.num_edges, batch, rank * batch, dev)     # weak scaling: B per GPU
+    B, T = acts.shape
+    gathered = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)         # > 126 MB L2
+
+    def step_dev():
+        out = ctx.reward_batch(acts, 0.5, args.mode, tdtype)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out["reward"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()                                  # evict L2 between timed iterations
+        ev[s][0].record()
+        out = step_dev()
+        ev[s][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.last_timing().launches * args.steps
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_ms)
+    value = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- per-kernel share + roofline (timing pass, device-resident inputs)
+    ctx.enable_timing(True)
+    ph = {"masks": 0.0, "transpose": 0.0, "reward": 0.0, "finalize": 0.0}
+    nrep = max(3, min(args.steps, 10))
+    for _ in range(nrep):
+        flush.zero_()
+        ctx.reward_batch(acts, 0.5, args.mode, tdtype)
+        tm = ctx.last_timing()
+        ph["masks"] += tm.ms_masks / nrep
+        ph["transpose"] += tm.ms_transpose / nrep
+        ph["reward"] += tm.ms_reward / nrep
+        ph["finalize"] += tm.ms_finalize / nrep
+    ctx.enable_timing(False)
+    g_bytes = algorithmic_bytes(ctx, p, acts, args.mode, wbytes) if rank == 0 else 0.0
+    W = (p.num_edges + 31) // 32
+    k0_bytes = float(B) * T * 8 + 2.0 * B * W * 4
+    peak, peak_src = measured_peak()
+    kern = {
+        "k0_masks(actions->kept bitmask)": {"ms": ph["masks"], "algorithmic_bytes": k0_bytes},
+        "k0_transpose+popcount": {"ms": ph["transpose"], "algorithmic_bytes": 3.0 * B * W * 4},
+        ("k3_copy_kernel" if args.mode == "copy" else "k2_ls_kernel"): {"ms": ph["reward"], "algorithmic_bytes": g_bytes},
+        "k3_finalize": {"ms": ph["finalize"], "algorithmic_bytes": 16.0 * B},
+    }
+    for v in kern.values():
+        v["gbps"] = v["algorithmic_bytes"] / max(v["ms"], 1e-9) / 1e6
+        v["share"] = v["ms"] / max(sum(ph.values()), 1e-9)
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbps"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbps"] / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "launch_ms": kern[dom]["ms"], "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
+                "note": "G counts every gathered entry (SURVEY.md 8d); the reward kernels re-use the gathered "
+                        "row tile across the 32 trajectories of a warp from shared memory, so G/time can exceed HBM peak"}
+
+    # ---- end to end through the host entry point (pinned host actions in, rewards out)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((B, T), dtype=torch.int64, pin_memory=True)
+        host.copy_(acts)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))   # syncs: result is on the host
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, r["reward"].to(dev))
+        e1.record()
+        barrier()
+        e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
+        t_e = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * args.steps / (float(t_e) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(B * T * 8), "d2h_bytes_per_step": int(B * 8),
+               "ms_per_step": float(t_e) / args.steps, "api": "SpaiContext.reward_batch(host int64 actions) "
+               "-> spai_reward_batch_host"}
+        del host
+
+    # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
+    extras = {}
+    if rank == 0 and not args.no_extras and args.mode == "copy":
+        sub = acts[: min(B, 1024)]
+        for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("copy", torch.float64)):
+            try:
+                for _ in range(2):
+                    ctx.reward_batch(sub, 0.5, md, dt)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(3):
+                    ctx.reward_batch(sub, 0.5, md, dt)
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / 3
+                extras[f"{md}/{'f32' if dt == torch.float32 else 'f64'}"] = {
+                    "patterns_per_s": sub.shape[0] / (ms / 1e3), "row_solves_per_s": sub.shape[0] * p.n / (ms / 1e3),
+                    "batch": int(sub.shape[0]), "ms": ms}
+            except Exception as exc:        # report, never hide
+                extras[f"{md}/{dt}"] = {"error": str(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1:
+        v, dt = cpu_port_throughput(args.config, args.scale, args.cpu_sample, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_sample} trajectories of the same workload, copy/fp32, numpy/scipy oracle "
+                         f"single process ({dt:.1f} s)"}
+
+    if rank == 0:
+        info = ctx.info()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args, p, B), "mode": args.mode, "n": p.n, "num_edges": p.num_edges,
+                       "batch_per_gpu": B, "max_trajectory_len": T, "alpha": 0.5,
+                       "parallelism": f"trajectory-sharded x{world}",
+                       "l2": "256 MiB flush between timed iterations; actions (B*T*8 B) exceed L2",
+                       "timing": "CUDA events per step on the launch stream, max over ranks"},
+            "row_solves_per_s": value * p.n,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kern,
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+            "extras": extras,
+            "context": {"setup_s": setup_s, "plan_contributions": int(info.contributions),
+                        "device_bytes": int(info.device_bytes), "max_row_union": int(info.max_row_union),
+                        "ls_class_rows": [int(x) for x in info.ls_class_rows]},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -693,7 +693,7 @@ enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
 static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t B, int64_t T, int64_t ld,
                          double alpha, int mode, int dtype, double* reward, double* residual,
                          int64_t* nnz_m, bool out_host, uint8_t* kept_bytes_dev, void* stream) {
-  if (!c || B < 0 || (B && !input) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS) ||
+  if (!c || B < 0 || (B && !input && (src == FROM_TAKEN_DEV || T > 0)) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS) ||
       (dtype != SPAI_F32 && dtype != SPAI_F64) || (src != FROM_TAKEN_DEV && (T < 0 || ld < T))) {
     set_error("reward: invalid arguments");
     return SPAI_ERR_INVALID;
