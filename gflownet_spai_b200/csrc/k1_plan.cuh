@@ -41,7 +41,7 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
                const T* __restrict__ slot_val, const int32_t* __restrict__ a_ptr,
                const int32_t* __restrict__ a_col, const T* __restrict__ a_val,
                const int64_t* __restrict__ cptr, int32_t* c_col, void* rec_copy_v, void* rec_ls_v,
-               int32_t* __restrict__ r_q, int32_t* __restrict__ r_diag) {
+               int32_t* __restrict__ r_q, int32_t* __restrict__ r_diag, RowHdr* __restrict__ rhdr) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -56,7 +56,11 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
     const int64_t c0 = cptr[i];
     const int64_t nci = cptr[i + 1] - c0;
     if (nci == 0) {
-      if (lane == 0) { r_q[i] = 0; r_diag[i] = -1; }
+      if (lane == 0) {
+        r_q[i] = 0; r_diag[i] = -1;
+        RowHdr h; h.cnt = 0; h.sp = sp; h.k = k; h.flags = 0;
+        rhdr[i] = h;
+      }
       continue;
     }
     // ---- pass 1: gather A rows, place every entry at its (x, e) rank
@@ -110,7 +114,8 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
       const unsigned hb = __ballot_sync(full, head);
       const int s = sbase + __popc(hb & (0xffffffffu >> (31 - lane))) - 1;
       if (valid) {
-        uint32_t fl = ((uint32_t)s << 16) | ((x == (int)i) ? F_DIAG : 0u) | ((next != x) ? F_END : 0u);
+        uint32_t fl = ((uint32_t)s << 16) | ((next != x) ? F_END : 0u) |
+                      ((next != x && next == (int)i) ? F_NEXT_DIAG : 0u);
         if constexpr (sizeof(T) == 4) {
           rc32[c0 + p].flags = __ldcg(&rc32[c0 + p].flags) | fl;
         } else {
@@ -123,7 +128,11 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
       if (db) diag = __shfl_sync(full, s, __ffs(db) - 1);
       sbase += __popc(hb);
     }
-    if (lane == 0) { r_q[i] = sbase; r_diag[i] = diag; }
+    if (lane == 0) {
+      r_q[i] = sbase; r_diag[i] = diag;
+      RowHdr h; h.cnt = (int32_t)nci; h.sp = sp; h.k = k; h.flags = (diag == 0) ? 1 : 0;
+      rhdr[i] = h;
+    }
   }
 }
 

@@ -8,149 +8,268 @@
 // of M, so every read of the row's gathered tile is a warp-uniform broadcast
 // from shared memory and control flow is uniform; the only per-lane state is
 // the row's kept-mask word and the running sums. A block owns a contiguous
-// range of rows (tiles of <= TILE_C plan records staged in shared memory) and
-// THREADS*NT trajectories; row sums are reduced in registers over the block's
-// rows, written once as partial[row_block][b], and combined in a fixed order
-// by the finalize kernel (deterministic, no atomics).
+// range of row tiles and THREADS*NT trajectories. Tiles (<= K3_TILE_C plan
+// records + their row headers) are brought into shared memory by
+// cp.async.bulk (TMA 1-D bulk copy) into a two-stage ring signalled through
+// mbarriers, so the copy of tile t+1 overlaps the arithmetic of tile t. Row
+// sums are reduced in registers over the block's rows, written once as
+// partial[row_block][b], and combined in a fixed order by the finalize kernel
+// (deterministic, no atomics).
 //
-// Per record: 1 broadcast LDS.128 + NT x (mask test, predicated add); per output
-// segment: NT x (subtract delta, FMA into the row sum).
+// Kept-mask words are read from maskT[w][b] (one coalesced 128-byte load per
+// warp and word) and carried in registers across the rows that share a word.
+//
+// Per record: 1 broadcast LDS.128 + NT x (bit test -> predicate, predicated
+// FADD); per output segment: NT x FFMA into the row sum (the accumulator starts
+// at -delta_ij, so no separate subtraction).
 #pragma once
 
 #include "spai_internal.cuh"
 
 namespace spai {
 
-constexpr int K3_TILE_C = 2048;      // records per staged tile (32 KB)
-constexpr int K3_THREADS = 256;
+constexpr int K3_TILE_C = 1024;      // records per staged tile (16 KB)
+constexpr int K3_TILE_R = 128;       // rows per staged tile (2 KB of headers)
+constexpr int K3_THREADS = 128;
+constexpr int K3_STAGE_BYTES = (K3_TILE_C + 1) * 16 + K3_TILE_R * 16;   // +1: prefetch slack
+constexpr int K3_SMEM_BYTES = 2 * K3_STAGE_BYTES + 64;
 
-template <typename T, int NT, typename Rec>
-__device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt, int sp, int k,
-                                            const uint32_t* __restrict__ maskT, int64_t Bp,
-                                            const int64_t (&b)[NT], double (&tot)[NT]) {
-  const int64_t w0 = sp >> 5;
-  const int sh = sp & 31;
-  const bool two = sh + k > 32;
-  const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-  uint32_t m[NT];
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void k3_cond_add(float& acc, uint32_t m, uint32_t ebit, float w) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.f32 %0, %0, %3;\n\t}"
+      : "+f"(acc)
+      : "r"(m), "r"(ebit), "f"(w));
+}
+__device__ __forceinline__ void k3_cond_add(double& acc, uint32_t m, uint32_t ebit, double w) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.f64 %0, %0, %3;\n\t}"
+      : "+d"(acc)
+      : "r"(m), "r"(ebit), "d"(w));
+}
+
+// The per-lane mask window: words wcur and wcur+1 of every trajectory handled by
+// the lane (trajectory j of the lane is column `j * K3_THREADS` after `mp`);
+// advanced monotonically as the rows walk through the slot range.
+template <int NT>
+struct MaskWindow {
+  int64_t wcur;
+  uint32_t lo[NT], hi[NT];
+  __device__ __forceinline__ void load(const uint32_t* __restrict__ mp, int64_t Bp, int64_t W, int64_t w) {
+    wcur = w;
+    const uint32_t* p0 = mp + w * Bp;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const uint32_t lo = maskT[w0 * Bp + b[j]];
-    const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b[j]] : 0u;
-    m[j] = __funnelshift_r(lo, hi, sh) & kmask;
-  }
-  T acc[NT], rs[NT];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) { acc[j] = T(0); rs[j] = T(0); }
-#pragma unroll 4
-  for (int c = 0; c < cnt; ++c) {
-    const Rec r = rp[c];
-    const T w = rec_w(r);
-#pragma unroll
-    for (int j = 0; j < NT; ++j) acc[j] += (m[j] & r.ebit) ? w : T(0);
-    if (r.flags & F_END) {
-      const T d = (r.flags & F_DIAG) ? T(1) : T(0);
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const T t = acc[j] - d;
-        rs[j] = fma(t, t, rs[j]);
-        acc[j] = T(0);
-      }
+    for (int j = 0; j < NT; ++j) {
+      lo[j] = (w < W) ? p0[j * K3_THREADS] : 0u;
+      hi[j] = (w + 1 < W) ? p0[Bp + j * K3_THREADS] : 0u;
     }
   }
+  __device__ __forceinline__ void seek(const uint32_t* __restrict__ mp, int64_t Bp, int64_t W, int64_t w) {
+    if (w == wcur) return;
+    if (w == wcur + 1) {
+      wcur = w;
+      const uint32_t* p1 = mp + (w + 1) * Bp;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) tot[j] += (double)rs[j];
+      for (int j = 0; j < NT; ++j) {
+        lo[j] = hi[j];
+        hi[j] = (w + 1 < W) ? p1[j * K3_THREADS] : 0u;
+      }
+      return;
+    }
+    load(mp, Bp, W, w);
+  }
+};
+
+// One row for NT trajectories per lane. The record stream is walked segment by
+// segment (do-while up to the END record: a real branch, so the per-segment
+// epilogue is not issued for every record). `rp[cnt]` may be read (prefetch);
+// callers guarantee one readable record past the end.
+template <typename T, int NT, typename Rec>
+__device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt, int sp, int k,
+                                            bool first_diag, MaskWindow<NT>& mw,
+                                            const uint32_t* __restrict__ mp, int64_t Bp, int64_t W,
+                                            T (&rs)[NT]) {
+  mw.seek(mp, Bp, W, sp >> 5);
+  const int sh = sp & 31;
+  const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  uint32_t m[NT];
+  T acc[NT];
+  const T a0 = first_diag ? T(-1) : T(0);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    m[j] = __funnelshift_r(mw.lo[j], mw.hi[j], sh) & kmask;
+    acc[j] = a0;
+  }
+  int c = 0;
+  Rec nx = rp[0];
+  while (c < cnt) {
+    Rec r;
+    do {
+      r = nx;
+      nx = rp[++c];
+      const T w = rec_w(r);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) k3_cond_add(acc[j], m[j], r.ebit, w);
+    } while (!(r.flags & F_END));
+    const T nxt = (r.flags & F_NEXT_DIAG) ? T(-1) : T(0);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      rs[j] = fma(acc[j], acc[j], rs[j]);
+      acc[j] = nxt;
+    }
+  }
 }
 
 // rows with more than 32 candidate slots: the kept bit of every record is read
 // from the mask on demand (coalesced across lanes; L1-resident within a row).
 template <typename T, int NT, typename Rec>
 __device__ __forceinline__ void k3_row_wide(const Rec* __restrict__ rp, int cnt, int sp,
-                                            const uint32_t* __restrict__ maskT, int64_t Bp,
-                                            const int64_t (&b)[NT], double (&tot)[NT]) {
-  T acc[NT], rs[NT];
+                                            bool first_diag, const uint32_t* __restrict__ mp,
+                                            int64_t Bp, T (&rs)[NT]) {
+  T acc[NT];
+  const T a0 = first_diag ? T(-1) : T(0);
 #pragma unroll
-  for (int j = 0; j < NT; ++j) { acc[j] = T(0); rs[j] = T(0); }
+  for (int j = 0; j < NT; ++j) acc[j] = a0;
   for (int c = 0; c < cnt; ++c) {
     const Rec r = rp[c];
     const T w = rec_w(r);
     const int64_t bit = (int64_t)sp + rec_e(r.flags);
-    const uint32_t* wp = maskT + (bit >> 5) * Bp;
+    const uint32_t* wp = mp + (bit >> 5) * Bp;
     const int sh = bit & 31;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) acc[j] += ((wp[b[j]] >> sh) & 1u) ? w : T(0);
+    for (int j = 0; j < NT; ++j) acc[j] += ((wp[j * K3_THREADS] >> sh) & 1u) ? w : T(0);
     if (r.flags & F_END) {
-      const T d = (r.flags & F_DIAG) ? T(1) : T(0);
+      const T nxt = (r.flags & F_NEXT_DIAG) ? T(-1) : T(0);
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const T t = acc[j] - d;
-        rs[j] = fma(t, t, rs[j]);
-        acc[j] = T(0);
+        rs[j] = fma(acc[j], acc[j], rs[j]);
+        acc[j] = nxt;
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < NT; ++j) tot[j] += (double)rs[j];
 }
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
-               const int32_t* __restrict__ sptr, const int32_t* __restrict__ tile_row, int ntiles,
-               const uint32_t* __restrict__ maskT, int64_t Bp, double* __restrict__ partial) {
+               const RowHdr* __restrict__ rhdr, const int32_t* __restrict__ tile_row, int ntiles,
+               const uint32_t* __restrict__ maskT, int64_t Bp, int64_t W,
+               double* __restrict__ partial) {
   using Rec = typename RecOf<T>::type;
-  extern __shared__ __align__(16) unsigned char k3_smem[];
-  Rec* tile = reinterpret_cast<Rec*>(k3_smem);
+  extern __shared__ __align__(128) unsigned char k3_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(k3_smem);                    // 2 mbarriers
+  unsigned char* stage0 = k3_smem + 64;
 
   const int t0 = (int)((int64_t)ntiles * blockIdx.x / gridDim.x);
   const int t1 = (int)((int64_t)ntiles * (blockIdx.x + 1) / gridDim.x);
+  // trajectory j of this lane: b = bbase + j*K3_THREADS + tid. maskT is padded to
+  // a multiple of K3_THREADS*NT columns by the host, so every column is readable.
   const int64_t bbase = (int64_t)blockIdx.y * (K3_THREADS * NT);
-  int64_t b[NT];
-  bool live[NT];
+  const uint32_t* mp = maskT + bbase + threadIdx.x;
   double tot[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) tot[j] = 0.0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // producer: one thread issues the bulk copies of a tile into stage s
+  auto issue = [&](int t, int s) {
+    const int r0 = tile_row[t], r1 = tile_row[t + 1];
+    const int64_t c0 = cptr[r0], c1 = cptr[r1];
+    unsigned char* st = stage0 + (size_t)s * K3_STAGE_BYTES;
+    const uint32_t hbytes = (uint32_t)(r1 - r0) * 16u;
+    const bool staged = (c1 - c0) <= K3_TILE_C;
+    const uint32_t rbytes = staged ? (uint32_t)(c1 - c0) * 16u : 0u;
+    mbar_expect_tx(&bars[s], hbytes + rbytes);
+    bulk_g2s(st + (K3_TILE_C + 1) * 16, rhdr + r0, hbytes, &bars[s]);
+    if (rbytes) bulk_g2s(st, recs + c0, rbytes, &bars[s]);
+  };
+
+  uint32_t phase[2] = {0u, 0u};
+  if (t0 < t1 && threadIdx.x == 0) issue(t0, 0);
+  MaskWindow<NT> mw;
+  mw.wcur = -2;
+  for (int t = t0; t < t1; ++t) {
+    const int s = (t - t0) & 1;
+    if (t + 1 < t1 && threadIdx.x == 0) issue(t + 1, s ^ 1);   // stage s^1 was released by the last sync
+    mbar_wait(&bars[s], phase[s]);
+    phase[s] ^= 1u;
+    const unsigned char* st = stage0 + (size_t)s * K3_STAGE_BYTES;
+    const Rec* tile = reinterpret_cast<const Rec*>(st);
+    const RowHdr* hdr = reinterpret_cast<const RowHdr*>(st + (K3_TILE_C + 1) * 16);
+    const int r0 = tile_row[t], r1 = tile_row[t + 1];
+    const int64_t c0 = cptr[r0];
+    const bool staged = (cptr[r1] - c0) <= K3_TILE_C;
+    T rs[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) rs[j] = T(0);
+    int off = 0;
+    for (int i = 0; i < r1 - r0; ++i) {
+      const RowHdr h = hdr[i];
+      if (h.cnt == 0) continue;
+      const bool fd = h.flags & 1;
+      if (h.k <= 32) {
+        if (staged) k3_row_fast<T, NT, Rec>(tile + off, h.cnt, h.sp, h.k, fd, mw, mp, Bp, W, rs);
+        else        k3_row_fast<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, h.k, fd, mw, mp, Bp, W, rs);
+      } else {
+        if (staged) k3_row_wide<T, NT, Rec>(tile + off, h.cnt, h.sp, fd, mp, Bp, rs);
+        else        k3_row_wide<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, fd, mp, Bp, rs);
+      }
+      off += h.cnt;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) tot[j] += (double)rs[j];   // fp32 sums live for one tile only
+    __syncthreads();                       // stage s fully consumed -> may be refilled
+  }
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const int64_t bj = bbase + (int64_t)j * K3_THREADS + threadIdx.x;
-    live[j] = bj < Bp;
-    b[j] = live[j] ? bj : 0;
-    tot[j] = 0.0;
+    if (bj < Bp) partial[(int64_t)blockIdx.x * Bp + bj] = tot[j];
   }
-
-  for (int t = t0; t < t1; ++t) {
-    const int r0 = tile_row[t], r1 = tile_row[t + 1];
-    const int64_t c0 = cptr[r0], c1 = cptr[r1];
-    const bool staged = (c1 - c0) <= K3_TILE_C;
-    __syncthreads();                       // previous tile fully consumed
-    if (staged) {
-      const int cnt = (int)(c1 - c0);
-      const uint4* src = reinterpret_cast<const uint4*>(recs + c0);
-      uint4* dst = reinterpret_cast<uint4*>(tile);
-      for (int x = threadIdx.x; x < cnt; x += K3_THREADS) dst[x] = __ldcs(src + x);
-    }
-    __syncthreads();
-    for (int i = r0; i < r1; ++i) {
-      const int64_t cb = cptr[i], ce = cptr[i + 1];
-      if (cb == ce) continue;
-      const int sp = sptr[i];
-      const int k = sptr[i + 1] - sp;
-      const int cnt = (int)(ce - cb);
-      if (k <= 32) {
-        if (staged) k3_row_fast<T, NT, Rec>(tile + (cb - c0), cnt, sp, k, maskT, Bp, b, tot);
-        else        k3_row_fast<T, NT, Rec>(recs + cb, cnt, sp, k, maskT, Bp, b, tot);
-      } else {
-        if (staged) k3_row_wide<T, NT, Rec>(tile + (cb - c0), cnt, sp, maskT, Bp, b, tot);
-        else        k3_row_wide<T, NT, Rec>(recs + cb, cnt, sp, maskT, Bp, b, tot);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NT; ++j)
-    if (live[j]) partial[(int64_t)blockIdx.x * Bp + b[j]] = tot[j];
 }
 
 // residual^2 = sum_g partial[g][b] + rows_missing_diag (each such row adds the
 // uncovered -1 of -I); residual = sqrt; reward mix of preconditioner.py:154-163
-// and :64, all in fp64. res2_in (optional) is added as well (generic-path sums).
+// and :64, all in fp64. res2_extra (optional) is added as well (generic-path sums).
 __global__ void k3_finalize_kernel(const double* __restrict__ partial, int nparts, int64_t Bp,
                                    int64_t B, const double* __restrict__ res2_extra,
                                    double rows_missing_diag, const long long* __restrict__ nnz,

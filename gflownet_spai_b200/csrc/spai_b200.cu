@@ -212,13 +212,14 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
   SPAI_TRY(ar.alloc(&plan.c_col, plan.nc));
   SPAI_TRY(ar.alloc(&plan.r_q, n));
   SPAI_TRY(ar.alloc(&plan.r_diag, n));
+  SPAI_TRY(ar.alloc(&plan.rhdr, n));
   if (dtype == SPAI_F32) {
     Rec32* r = nullptr;
-    SPAI_TRY(ar.alloc(&r, plan.nc));
+    SPAI_TRY(ar.alloc(&r, plan.nc + 1));          // +1: the copy kernel prefetches one record ahead
     plan.rec_copy = r; plan.rec_ls = r;
   } else {
     Rec64* r = nullptr;
-    SPAI_TRY(ar.alloc(&r, plan.nc));
+    SPAI_TRY(ar.alloc(&r, plan.nc + 1));
     plan.rec_copy = r;
     if (want_ls) { Rec64* l = nullptr; SPAI_TRY(ar.alloc(&l, plan.nc)); plan.rec_ls = l; }
   }
@@ -226,10 +227,10 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 8), 148 * 64);
     if (dtype == SPAI_F32)
       k1_fill_kernel<float><<<blocks, 256, 0, st>>>(n, P.sptr, P.slot_col, P.slot_val32, A.ptr, A.col, A.val32,
-                                                   plan.cptr, plan.c_col, plan.rec_copy, nullptr, plan.r_q, plan.r_diag);
+                                                   plan.cptr, plan.c_col, plan.rec_copy, nullptr, plan.r_q, plan.r_diag, plan.rhdr);
     else
       k1_fill_kernel<double><<<blocks, 256, 0, st>>>(n, P.sptr, P.slot_col, P.slot_val64, A.ptr, A.col, A.val64,
-                                                    plan.cptr, plan.c_col, plan.rec_copy, plan.rec_ls, plan.r_q, plan.r_diag);
+                                                    plan.cptr, plan.c_col, plan.rec_copy, plan.rec_ls, plan.r_q, plan.r_diag, plan.rhdr);
     SPAI_CUDA(cudaGetLastError());
   }
   std::vector<int32_t> hq(n), hd(n);
@@ -245,7 +246,7 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
     const int64_t c = hc[i];
     if (acc > 0 && acc + c > K3_TILE_C) { tiles.push_back((int32_t)i); acc = 0; }
     acc += c;
-    if (i - tiles.back() >= 4096) { tiles.push_back((int32_t)(i + 1)); acc = 0; }
+    if (i + 1 - tiles.back() >= K3_TILE_R) { tiles.push_back((int32_t)(i + 1)); acc = 0; }
   }
   if (tiles.back() != n) tiles.push_back((int32_t)n);
   plan.ntiles = (int)tiles.size() - 1;
@@ -308,22 +309,28 @@ struct Carver {
 };
 static inline int64_t padded(int64_t bytes) { return round_up(bytes, 256) + 256; }
 
-struct EvalShape {       // launch geometry of one reward evaluation over Bp trajectories
+struct EvalShape {       // launch geometry of one reward evaluation over Bc trajectories
+  int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
   int nt = 1, gx = 1, gy = 1;                       // copy kernel
   int ls_gx[LS_NCLASS] = {}, ls_gy[LS_NCLASS] = {}, ls_ntg[LS_NCLASS] = {};
   int parts = 1;
   int64_t generic_work = 0, generic_cmap = 0, generic_warps = 0;
 };
 
-static EvalShape plan_shape(const Plan& plan, int mode, int64_t Bp, int sm_count) {
+static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, int sm_count) {
   EvalShape s;
   if (mode == SPAI_MODE_COPY) {
-    s.nt = (Bp >= 2048) ? 4 : (Bp >= 512 ? 2 : 1);
+    s.nt = (Bc >= 1024) ? 8 : (Bc >= 512 ? 4 : (Bc >= 256 ? 2 : 1));
+    if (dtype == SPAI_F64 && s.nt > 4) s.nt = 4;
+    s.Bp = round_up(Bc, (int64_t)K3_THREADS * s.nt);
+    const int64_t Bp = s.Bp;
     s.gy = (int)ceil_div(Bp, (int64_t)K3_THREADS * s.nt);
     const int target = sm_count * 8;
     s.gx = (int)std::max<int64_t>(1, std::min<int64_t>(plan.ntiles, std::max(1, target / s.gy)));
     s.parts = s.gx;
   } else {
+    s.Bp = round_up(Bc, 32);
+    const int64_t Bp = s.Bp;
     s.parts = 0;
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
       if (!plan.class_count[c]) continue;
@@ -345,7 +352,8 @@ static EvalShape plan_shape(const Plan& plan, int mode, int64_t Bp, int sm_count
   return s;
 }
 
-static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int64_t Bp, int dtype) {
+static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int dtype) {
+  const int64_t Bp = s.Bp;
   int64_t b = padded(W * Bp * 4)              // maskT
               + padded(Bp * 8)                 // nnz
               + padded((int64_t)s.parts * Bp * 8)
@@ -406,8 +414,8 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
                       double res0, double flops0, double alpha, double* reward, double* residual,
                       int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches) {
   const int64_t W = P.words();
-  const int64_t Bp = round_up(Bc, 32);
-  const EvalShape s = plan_shape(plan, mode, Bp, sm_count);
+  const EvalShape s = plan_shape(plan, mode, dtype, Bc, sm_count);
+  const int64_t Bp = s.Bp;
   Carver cv{scratch, scratch + scratch_bytes};
   uint32_t* maskT = cv.take<uint32_t>(W * Bp);
   long long* nnz = cv.take<long long>(Bp);
@@ -433,15 +441,16 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   int parts = s.parts;
   if (mode == SPAI_MODE_COPY) {
     const dim3 grid(s.gx, s.gy);
-    const size_t smem = (size_t)K3_TILE_C * 16;
+    const size_t smem = (size_t)K3_SMEM_BYTES;
 #define SPAI_K3(T, NT)                                                                          \
   k3_copy_kernel<T, NT><<<grid, K3_THREADS, smem, st>>>(                                        \
-      reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, P.sptr,       \
-      plan.tile_row, plan.ntiles, maskT, Bp, partial)
+      reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, plan.rhdr,    \
+      plan.tile_row, plan.ntiles, maskT, Bp, W, partial)
     if (plan.ntiles == 0) {
       SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)s.parts * Bp * 8, st));
     } else if (dtype == SPAI_F32) {
-      if (s.nt == 4) SPAI_K3(float, 4); else if (s.nt == 2) SPAI_K3(float, 2); else SPAI_K3(float, 1);
+      if (s.nt == 8) SPAI_K3(float, 8); else if (s.nt == 4) SPAI_K3(float, 4);
+      else if (s.nt == 2) SPAI_K3(float, 2); else SPAI_K3(float, 1);
     } else {
       if (s.nt == 4) SPAI_K3(double, 4); else if (s.nt == 2) SPAI_K3(double, 2); else SPAI_K3(double, 1);
     }
@@ -544,8 +553,8 @@ static int residual_all_kept(const Pattern& P, const Plan& plan, int dtype, int 
     k0_mask_init_kernel<<<(unsigned)std::min<int64_t>(ceil_div(W, 256), 65535), 256, 0, st>>>(mask, W, P.E, 1);
     SPAI_CUDA(cudaGetLastError());
   }
-  const EvalShape s = plan_shape(plan, SPAI_MODE_COPY, 32, sm_count);
-  const int64_t need = eval_bytes(plan, s, W, 32, dtype);
+  const EvalShape s = plan_shape(plan, SPAI_MODE_COPY, dtype, 1, sm_count);
+  const int64_t need = eval_bytes(plan, s, W, dtype);
   char* scratch = nullptr;
   SPAI_TRY(tmp.alloc(&scratch, need));
   SPAI_TRY(eval_masks(P, plan, SPAI_MODE_COPY, dtype, mask, 1, scratch, need, sm_count, (double)P.n, 1.0,
@@ -715,7 +724,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4);                 // mask
     if (src == FROM_ACTIONS_HOST) need += padded(bc * ld * 8);
     if (out_host) need += 3 * padded(bp * 8);
-    if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, bp, c->sm_count), W, bp, dtype);
+    if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, dtype, bc, c->sm_count), W, dtype);
     return need;
   };
   while (Bc > 32 && need_for(Bc) > c->ws_limit) Bc = std::max<int64_t>(32, round_up(Bc / 2, 32));

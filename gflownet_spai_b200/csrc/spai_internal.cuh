@@ -39,11 +39,12 @@ void set_error(const char* fmt, ...);
 // by (x, e); records with the same x form one output segment (one entry of the
 // row of M*A). 16 bytes, so a run of records is a legal cp.async.bulk source.
 //   flags: bit0 END  last record of its output segment
-//          bit1 DIAG the segment's column is the row index (the "-I" entry)
+//          bit1 NEXT_DIAG (END records only) the FOLLOWING segment's column is
+//               the row index, i.e. the entry that carries the "-1" of "-I"
 //          bits 2..15  e  slot index inside the row (< 16384)
 //          bits 16..31 s  output segment index inside the row (< 65536)
 constexpr uint32_t F_END = 1u;
-constexpr uint32_t F_DIAG = 2u;
+constexpr uint32_t F_NEXT_DIAG = 2u;
 constexpr int MAX_ROW_SLOTS = 16384;
 constexpr int MAX_ROW_UNION = 65536;
 
@@ -60,6 +61,13 @@ struct alignas(16) Rec64 {
   uint32_t ebit;
   uint32_t flags;
   double v;        // w (copy plan) or a (ls plan)
+};
+// Row header (16 bytes, bulk-copied next to the records of its tile).
+struct alignas(16) RowHdr {
+  int32_t cnt;     // records of the row
+  int32_t sp;      // first slot of the row == its bit offset in the kept-mask
+  int32_t k;       // candidate slots of the row
+  int32_t flags;   // bit0: the row's first output segment is the diagonal
 };
 template <typename T> struct RecOf;
 template <> struct RecOf<float> { using type = Rec32; };
@@ -110,6 +118,7 @@ struct Plan {
   void* rec_ls = nullptr;         // Rec32 (same array) / Rec64(a)
   int32_t* r_q = nullptr;         // [n] |I_i|
   int32_t* r_diag = nullptr;      // [n] segment index of column i, or -1
+  RowHdr* rhdr = nullptr;         // [n]
   int64_t rows_missing_diag = 0;  // rows with r_diag < 0 (each adds 1 to ||.||^2)
   int max_q = 0;
   // copy-kernel tiling: tile t = rows [tile_row[t], tile_row[t+1])

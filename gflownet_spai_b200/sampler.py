@@ -1,0 +1,190 @@
+"""Drop-in `GFlowNet` sampler, `Log` and trajectory-balance loss.
+
+Mirrors the reference's
+  * gflownet/gflownet.py:12-197  (GFlowNet, forward_probs, sample_states)
+  * gflownet/log.py:10-164       (Log)
+  * gflownet/utils.py:228-278    (trajectory_balance_loss)
+with the masked-categorical environment step (policy.py:64-73,
+gflownet.py:116-119,:148,:177-179, log.py:67-87) executed by CUDA kernel K4 and
+the batch reward by the SPAI reward kernels.
+
+Why one policy call per epoch is enough: inside `sample_states` the graph and
+the weights are identical for every sample and every step (states are never
+mutated, gflownet.py:164-172), so the policy's pre-mask distribution p is one
+vector; masking taken ids and re-normalising gives, for an untaken id a,
+    softmax(masked logits)[a] = p[a] / (1 - sum_{taken} p).
+The sampler therefore evaluates the policy once (with autograd), draws all
+steps on the device from log(p), and rebuilds the chosen-action probabilities
+as a differentiable function of p for the loss.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from .env import Data
+
+__all__ = ["GFlowNet", "Log", "trajectory_balance_loss"]
+
+
+def trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs):
+    """Mean trajectory-balance loss with the reference's stabilisation
+    (gflownet/utils.py:228-278): eps = 1e-9 inside every log, per-side
+    subtraction of the batch maximum of the summed log-probabilities."""
+    eps = 1e-9
+    dt, dev = fwd_probs.dtype, fwd_probs.device
+    total_flow = total_flow.to(dev).to(dt)
+    rewards = rewards.to(dev).to(dt)
+    back_probs = back_probs.to(dev).to(dt)
+    lf = torch.log(fwd_probs + eps).sum(dim=-1)
+    lb = torch.log(back_probs + eps).sum(dim=-1)
+    lf = lf - lf.max(dim=0, keepdim=True)[0]
+    lb = lb - lb.max(dim=0, keepdim=True)[0]
+    lhs = torch.log(total_flow + eps) + lf
+    rhs = torch.log(rewards + eps) + lb
+    return ((lhs - rhs) ** 2).mean()
+
+
+class Log:
+    """gflownet/log.py:10-164: per-step chosen-action probabilities and actions
+    (-1 once a sample has finished), rewards, lazy backward probabilities."""
+
+    def __init__(self, s0, backward_policy, total_flow, env):
+        self._fwd_probs = []
+        self._back_probs = None
+        self._actions = []
+        self.rewards = torch.zeros(len(s0))
+        self.backward_policy = backward_policy
+        self.total_flow = total_flow
+        self.env = env
+        self.num_samples = len(s0)
+
+    def log(self, s, probs: torch.Tensor, actions: torch.Tensor, done: torch.Tensor):
+        """log.py:24-89 (host tensors; the device sampler fills the log directly)."""
+        chosen = probs.gather(2, actions.unsqueeze(1)).reshape(-1)
+        active = ~done.flatten().bool()
+        fwd = torch.ones(actions.shape[0], device=actions.device, dtype=chosen.dtype)
+        fwd[active] = chosen[active]
+        self._fwd_probs.append(fwd)
+        rec = -torch.ones(self.num_samples, dtype=torch.long)
+        rec[active] = actions.reshape(-1)[active]
+        self._actions.append(rec)
+
+    @property
+    def fwd_probs(self):
+        if isinstance(self._fwd_probs, list):
+            self._fwd_probs = torch.stack(self._fwd_probs, dim=0).t()
+        return self._fwd_probs
+
+    @property
+    def actions(self):
+        if isinstance(self._actions, list):
+            self._actions = torch.stack(self._actions, dim=0)
+        return self._actions
+
+    @property
+    def back_probs(self):
+        if self._back_probs is None:
+            back = self.backward_policy(self.actions.t())
+            self._back_probs = back.reshape(self.num_samples, -1)
+        return self._back_probs
+
+
+class GFlowNet(nn.Module):
+    """gflownet/gflownet.py:12-197 with the step loop on the GPU."""
+
+    def __init__(self, forward_policy, backward_policy, env):
+        super().__init__()
+        self.register_buffer("total_flow", torch.ones(1))      # gflownet.py:16 (not learned)
+        self.forward_policy = forward_policy
+        self.backward_policy = backward_policy
+        self.env = env
+        self.check_every = 8
+
+    # ------------------------------------------------------------------ reference protocol
+    def state_to_data(self, s: List[torch.Tensor]) -> list:
+        """gflownet.py:223-257."""
+        out = []
+        for i, m in enumerate(s):
+            if not m.is_sparse:
+                raise ValueError(f"Tensor at index {i} is not a sparse tensor.")
+            x = torch.ones((self.env.matrix_size * 2, 1))
+            out.append(Data(x=x, edge_index=m._indices(), edge_attr=m._values().float()))
+        return out
+
+    def forward_probs(self, s, data_list, actions=None):
+        """gflownet.py:47-123: ([B, 1, A] probabilities, mean alpha); one policy
+        call per sample, renormalised only when B > 1."""
+        if actions is None or len(actions) == 0:
+            acts = torch.empty(0)
+        else:
+            acts = torch.tensor(list(zip(*actions)), dtype=torch.long)
+        probs, alphas = [], []
+        for i, data in enumerate(data_list):
+            a_i = acts[i, :] if acts.numel() > 0 else torch.empty(0, dtype=torch.long)
+            p, al = self.forward_policy(data, a_i)
+            probs.append(p)
+            alphas.append(al)
+        probs = torch.stack(probs, dim=0)
+        alpha = torch.stack(alphas, dim=0).mean()
+        if probs.size(0) > 1:
+            tot = probs.sum(2)
+            tot = torch.where(tot == 0, torch.ones_like(tot), tot)
+            probs = probs / tot.unsqueeze(1)
+        return probs, alpha
+
+    # ------------------------------------------------------------------ device sampler
+    @staticmethod
+    def chosen_probs(p: torch.Tensor, actions_bt: torch.Tensor) -> torch.Tensor:
+        """Differentiable probabilities of the drawn actions: p[a_t] divided by the
+        mass not yet taken before step t; 1.0 where the action is -1."""
+        valid = actions_bt >= 0
+        idx = actions_bt.clamp(min=0)
+        pa = p.to(torch.float64)[idx] * valid
+        before = torch.cumsum(pa, dim=1) - pa
+        out = pa / (1.0 - before).clamp_min(1e-300)
+        return torch.where(valid, out, torch.ones_like(out)).to(p.dtype)
+
+    def sample_states(self, s0, return_log=False, generator: torch.Generator | None = None):
+        """gflownet.py:125-197. Returns the Log (or None), as the reference does."""
+        bsz = len(s0)
+        ctx = self.env.ctx
+        dev = torch.device("cuda", ctx.device)
+        log = Log(s0, self.backward_policy, self.total_flow, self.env) if return_log else None
+        data = self.state_to_data(s0[:1])[0]
+        p, alpha = self.forward_policy(data, torch.empty(0, dtype=torch.long))   # [1, A], with autograd
+        p = p.reshape(-1)
+        a = p.numel()
+        logits = torch.log(p.detach().to(dev, torch.float32).clamp_min(1e-45)).contiguous()
+        words = (a + 31) // 32
+        taken = torch.zeros((bsz, words), dtype=torch.int32, device=dev)
+        done = torch.zeros(bsz, dtype=torch.uint8, device=dev)
+        acts, probs = [], []
+        step = 0
+        while True:
+            u = torch.rand(bsz, device=dev, generator=generator)
+            act = torch.empty(bsz, dtype=torch.int64, device=dev)
+            pr = torch.empty(bsz, dtype=torch.float32, device=dev)
+            ctx.sample_step(logits, taken, u, done, act, pr)
+            acts.append(act)
+            probs.append(pr)
+            step += 1
+            if step % self.check_every == 0 or step > a:
+                if bool(done.all()):
+                    break
+        actions_tb = torch.stack(acts, dim=0)                     # [T', B]
+        live = (actions_tb >= 0).any(dim=1)
+        t_len = int(live.sum())                                   # drop all-finished trailing steps
+        actions_tb = actions_tb[:t_len].contiguous()
+        complete_actions = actions_tb.t().contiguous()            # [B, T] on the device
+        al = float(alpha.detach()) if isinstance(alpha, torch.Tensor) else float(alpha)
+        rewards = self.env.update_tensor(complete_actions, al, want=("reward",))["reward"]
+        if log is not None:
+            log._actions = actions_tb.cpu()
+            log._fwd_probs = self.chosen_probs(p, complete_actions.to(p.device))
+            log.sampled_probs = torch.stack(probs[:t_len], dim=0).t().cpu()   # K4's own fp32 values
+            log.rewards = rewards.to(torch.float32).cpu()
+            log.alpha = alpha
+        return log if return_log else None

@@ -1,0 +1,134 @@
+"""K4 (masked categorical step) and the device sampling loop."""
+import numpy as np
+import pytest
+import torch
+
+from gflownet_spai_b200 import synth
+from oracle import spai_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_env():
+    from gflownet_spai_b200.env import PreconditionerEnv
+    p = synth.make_problem("cfg1")
+    init = torch.sparse_coo_tensor(torch.tensor(np.stack([p.edge_row, p.edge_col])),
+                                   torch.tensor(p.edge_val, dtype=torch.float32), (p.n, p.n))
+    env = PreconditionerEnv(p.n, init, init.clone())
+    yield env, init
+    env.ctx.close()
+
+
+def _pack(taken_lists, a):
+    words = (a + 31) // 32
+    out = np.zeros((len(taken_lists), words), dtype=np.uint32)
+    for b, ids in enumerate(taken_lists):
+        for i in ids:
+            out[b, i // 32] |= np.uint32(1) << np.uint32(i % 32)
+    return torch.from_numpy(out.view(np.int32)).cuda()
+
+
+@pytest.mark.parametrize("a", [5, 461, 4099])
+def test_sample_step_matches_inverse_cdf_oracle(small_env, a):
+    env, _ = small_env
+    rng = np.random.default_rng(a)
+    bsz = 96
+    logits = rng.normal(scale=2.0, size=a).astype(np.float32)
+    taken_lists = [list(rng.choice(a - 1, size=int(rng.integers(0, a - 1)), replace=False)) for _ in range(bsz)]
+    done0 = rng.random(bsz) < 0.2
+    u = rng.random(bsz).astype(np.float32)
+    taken = _pack(taken_lists, a)
+    before = taken.clone()
+    done = torch.from_numpy(done0.astype(np.uint8)).cuda()
+    act = torch.empty(bsz, dtype=torch.int64, device="cuda")
+    prob = torch.empty(bsz, dtype=torch.float32, device="cuda")
+    env.ctx.sample_step(torch.from_numpy(logits).cuda(), taken, torch.from_numpy(u).cuda(), done, act, prob)
+    act, prob, done = act.cpu().numpy(), prob.cpu().numpy(), done.cpu().numpy().astype(bool)
+    for b in range(bsz):
+        if done0[b]:
+            assert act[b] == -1 and prob[b] == 1.0 and done[b]
+            assert torch.equal(taken[b], before[b])
+            continue
+        p = orc.masked_softmax_probs(logits, taken_lists[b]).astype(np.float64)
+        cdf = np.cumsum(p)
+        x = int(act[b])
+        assert 0 <= x < a and x not in taken_lists[b]            # never re-select a taken id
+        lo = cdf[x - 1] if x else 0.0
+        tgt = float(u[b]) * cdf[-1]
+        assert lo - 1e-5 <= tgt <= cdf[x] + 1e-5                  # inverse-CDF interval (fp32 sums)
+        assert prob[b] == pytest.approx(p[x] / cdf[-1], rel=2e-4, abs=1e-7)
+        assert done[b] == (x == a - 1)                            # terminal id = A-1
+        assert (int(taken[b, x // 32]) >> (x % 32)) & 1          # state updated in place
+
+
+def test_sample_step_distribution_chi_square(small_env):
+    env, _ = small_env
+    a, bsz = 9, 40000
+    logits = torch.log(torch.tensor([0.05, 0.2, 0.05, 0.1, 0.1, 0.15, 0.05, 0.2, 0.1]))
+    taken = _pack([[2, 6]] * bsz, a)
+    done = torch.zeros(bsz, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.rand(bsz, device="cuda", generator=g)
+    act = torch.empty(bsz, dtype=torch.int64, device="cuda")
+    prob = torch.empty(bsz, dtype=torch.float32, device="cuda")
+    env.ctx.sample_step(logits.cuda(), taken, u, done, act, prob)
+    counts = np.bincount(act.cpu().numpy(), minlength=a).astype(np.float64)
+    p = orc.masked_softmax_probs(logits.numpy(), [2, 6]).astype(np.float64)
+    assert counts[2] == 0 and counts[6] == 0
+    keep = p > 0
+    chi2 = float(((counts[keep] - bsz * p[keep]) ** 2 / (bsz * p[keep])).sum())
+    assert chi2 < 27.9                                            # chi2(6 dof) 99.99th percentile
+
+
+class _StubForward(torch.nn.Module):
+    """Stand-in for policy.ForwardPolicy (GATv2Conv is unavailable): same
+    call signature and return convention (probs [1, A], sigmoid(alpha))."""
+
+    def __init__(self, a):
+        super().__init__()
+        self.logit = torch.nn.Parameter(torch.linspace(-1.0, 1.0, a))
+        self.alpha = torch.nn.Parameter(torch.tensor(0.0))
+
+    def forward(self, data, actions):
+        x = self.logit[None, : data.edge_attr.size(0) + 1]
+        if actions.numel() > 0:
+            m = torch.ones_like(x, dtype=torch.bool)
+            m[:, actions] = 0
+            x = x.masked_fill(~m, float("-inf"))
+        return torch.softmax(x, dim=1), torch.sigmoid(self.alpha)
+
+
+class _StubBackward(torch.nn.Module):
+    def forward(self, trajectories):
+        return torch.full(trajectories.shape, 0.5)
+
+
+def test_sample_states_device_loop(small_env):
+    from gflownet_spai_b200.sampler import GFlowNet, trajectory_balance_loss
+    env, init = small_env
+    a = env.num_actions
+    fp = _StubForward(a)
+    with torch.no_grad():
+        fp.logit[-1] = 3.0                       # make termination likely so trajectories stay short
+    model = GFlowNet(fp, _StubBackward(), env)
+    bsz = 16
+    s0 = [init.clone() for _ in range(bsz)]
+    log = model.sample_states(s0, return_log=True, generator=torch.Generator(device="cuda").manual_seed(3))
+    acts = log.actions                           # [T, B]
+    assert acts.shape[1] == bsz and log.fwd_probs.shape == (bsz, acts.shape[0])
+    assert len(log._actions) == acts.shape[0]
+    for b in range(bsz):
+        col = acts[:, b].tolist()
+        valid = [x for x in col if x != -1]
+        assert valid[-1] == a - 1 and len(set(valid)) == len(valid)        # ends at terminal, no repeats
+        assert all(x == -1 for x in col[len(valid):])                      # -1 only after the terminal
+    # rewards equal a fresh evaluation of the logged actions (gflownet.py:181-195)
+    again = torch.tensor(env.update(s0, acts.t(), 0.5), dtype=torch.float32)
+    assert torch.allclose(log.rewards, again, rtol=1e-5, atol=1e-3)
+    # differentiable chosen probabilities agree with K4's own fp32 values
+    assert torch.allclose(log.fwd_probs.detach().float(), log.sampled_probs, rtol=2e-3, atol=1e-6)
+    loss = trajectory_balance_loss(log.total_flow, log.rewards.clamp_min(1e-3), log.fwd_probs, log.back_probs)
+    loss.backward()
+    assert torch.isfinite(fp.logit.grad).all() and float(fp.logit.grad.abs().sum()) > 0
+    assert model.sample_states(s0, return_log=False) is None
