@@ -51,7 +51,7 @@ class SpaiTiming(C.Structure):
         ("ms_masks", C.c_float), ("ms_transpose", C.c_float), ("ms_reward", C.c_float),
         ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32),
         ("chunks", C.c_int32), ("algorithmic_bytes", C.c_double),
-        ("compulsory_bytes", C.c_double),
+        ("compulsory_bytes", C.c_double), ("h2d_bytes", C.c_double),
     ]
 
 

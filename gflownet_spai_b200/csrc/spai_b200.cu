@@ -3,7 +3,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 #include "k0_masks.cuh"
 #include "k1_plan.cuh"
@@ -695,6 +698,52 @@ int spai_ctx_last_timing(const spai_ctx* c, spai_timing* out) {
 
 namespace spai {
 
+// Host side of spai_reward_batch_host: find, for every row of the -1 padded
+// action matrix, the length of the prefix that still holds ids (scan back from
+// the end over the padding), so only that prefix crosses PCIe. Exact for any
+// input (-1 anywhere else is simply copied and ignored by the kernels).
+static inline int64_t trimmed_len(const int64_t* row, int64_t T) {
+  int64_t t = T;
+  while (t >= 8) {
+    const int64_t* q = row + t - 8;
+    if ((q[0] & q[1] & q[2] & q[3] & q[4] & q[5] & q[6] & q[7]) != -1) break;
+    t -= 8;
+  }
+  while (t > 0 && row[t - 1] == -1) --t;
+  return t;
+}
+
+struct RowTrimmer {          // worker threads publish lengths group by group
+  static constexpr int64_t GROUP = 16;
+  std::vector<int32_t> len;
+  std::vector<std::atomic<int>> ready;
+  std::vector<std::thread> workers;
+  RowTrimmer(const int64_t* base, int64_t B, int64_t T, int64_t ld)
+      : len(B), ready((size_t)ceil_div(std::max<int64_t>(B, 1), GROUP)) {
+    for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("SPAI_HOST_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(nt, 32));
+    const int64_t ngroups = (int64_t)ready.size();
+    nt = (int)std::min<int64_t>(nt, ngroups);
+    auto next = std::make_shared<std::atomic<int64_t>>(0);
+    for (int w = 0; w < nt; ++w)
+      workers.emplace_back([this, base, B, T, ld, ngroups, next]() {
+        for (;;) {
+          const int64_t g = next->fetch_add(1);
+          if (g >= ngroups) return;
+          const int64_t hi = std::min(B, (g + 1) * GROUP);
+          for (int64_t b = g * GROUP; b < hi; ++b) len[b] = (int32_t)trimmed_len(base + b * ld, T);
+          ready[g].store(1, std::memory_order_release);
+        }
+      });
+  }
+  void wait(int64_t g) {
+    while (!ready[g].load(std::memory_order_acquire)) std::this_thread::yield();
+  }
+  ~RowTrimmer() { for (auto& t : workers) t.join(); }
+};
+
 enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
 
 // Shared driver of the three reward entry points: chunk the batch so the scratch
@@ -722,7 +771,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   auto need_for = [&](int64_t bc) {
     const int64_t bp = round_up(bc, 32);
     int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4);                 // mask
-    if (src == FROM_ACTIONS_HOST) need += padded(bc * ld * 8);
+    if (src == FROM_ACTIONS_HOST) need += padded(bc * std::max<int64_t>(T, 1) * 8) + padded(bc * 4);
     if (out_host) need += 3 * padded(bp * 8);
     if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, dtype, bc, c->sm_count), W, dtype);
     return need;
@@ -732,6 +781,9 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   SPAI_TRY(c->ws.ensure(need));
   (void)Bp_all;
 
+  std::unique_ptr<RowTrimmer> trimmer;      // keeps the host length array alive until the stream is drained
+  int64_t trimmer_b0 = -1;
+  double h2d_bytes = 0;
   PhaseTimer* pt = &c->pt;
   float ms_masks = 0, ms_tr = 0, ms_rw = 0, ms_fin = 0;
   int launches = 0, chunks = 0;
@@ -742,10 +794,36 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     Carver cv{reinterpret_cast<char*>(c->ws.base), reinterpret_cast<char*>(c->ws.base) + c->ws.bytes};
     uint32_t* mask = cv.take<uint32_t>(bc * std::max<int64_t>(W, 1));
     const int64_t* act_dev = nullptr;
+    int64_t act_ld = ld;
+    const int32_t* row_len_dev = nullptr;
     if (src == FROM_ACTIONS_HOST) {
-      int64_t* buf = cv.take<int64_t>(bc * ld);
-      SPAI_CUDA(cudaMemcpyAsync(buf, reinterpret_cast<const int64_t*>(input) + b0 * ld, (size_t)bc * ld * 8,
-                                cudaMemcpyHostToDevice, st));
+      int64_t* buf = cv.take<int64_t>(bc * std::max<int64_t>(T, 1));
+      int32_t* len_dev = cv.take<int32_t>(bc);
+      const int64_t* hbase = reinterpret_cast<const int64_t*>(input) + b0 * ld;
+      act_ld = T;
+      if (T >= 4096) {
+        // overlap: workers trim rows while this thread enqueues the prefix copies
+        if (!trimmer || trimmer_b0 != b0) { trimmer.reset(new RowTrimmer(hbase, bc, T, ld)); trimmer_b0 = b0; }
+        for (int64_t g = 0; g * RowTrimmer::GROUP < bc; ++g) {
+          trimmer->wait(g);
+          const int64_t hi = std::min(bc, (g + 1) * RowTrimmer::GROUP);
+          for (int64_t b = g * RowTrimmer::GROUP; b < hi; ++b) {
+            const int64_t n = trimmer->len[b];
+            if (n) SPAI_CUDA(cudaMemcpyAsync(buf + b * T, hbase + b * ld, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+          }
+        }
+        SPAI_CUDA(cudaMemcpyAsync(len_dev, trimmer->len.data(), (size_t)bc * 4, cudaMemcpyHostToDevice, st));
+        row_len_dev = len_dev;
+        h2d_bytes += (double)bc * 4;
+        for (int64_t b = 0; b < bc; ++b) h2d_bytes += 8.0 * trimmer->len[b];
+      } else if (ld == T) {
+        SPAI_CUDA(cudaMemcpyAsync(buf, hbase, (size_t)bc * T * 8, cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double)bc * T * 8;
+      } else {
+        SPAI_CUDA(cudaMemcpy2DAsync(buf, (size_t)T * 8, hbase, (size_t)ld * 8, (size_t)T * 8, (size_t)bc,
+                                    cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double)bc * T * 8;
+      }
       act_dev = buf;
     } else if (src == FROM_ACTIONS_DEV) {
       act_dev = reinterpret_cast<const int64_t*>(input) + b0 * ld;
@@ -766,17 +844,31 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
             P.E, mask, W, bc);
         SPAI_CUDA(cudaGetLastError()); ++launches;
       } else {
-        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
-        k0_mask_init_kernel<<<blocks, 256, 0, st>>>(mask, W, P.E, bc);
-        SPAI_CUDA(cudaGetLastError()); ++launches;
-        if (T > 0) {
-          constexpr int U = 4;
-          const int64_t chunks_t = ceil_div(T, 256 * U);
-          const int64_t nblk = chunks_t * bc;
-          if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
-          k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
-              act_dev, bc, T, ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t);
+        // variant: shared-memory bitmask per trajectory when it fits, else global RED
+        static const int k0_variant = [] {
+          const char* v = getenv("SPAI_K0_VARIANT");
+          return !v ? 0 : (!strcmp(v, "red") ? 1 : (!strcmp(v, "smem") ? 2 : 0));
+        }();
+        const bool fits = W * 4 <= K0S_MAX_SMEM;
+        if (fits && k0_variant != 1 && T > 0) {
+          SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         K0S_MAX_SMEM));
+          k0_mask_build_smem_kernel<<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(
+              act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nullptr, row_len_dev);
           SPAI_CUDA(cudaGetLastError()); ++launches;
+        } else {
+          const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
+          k0_mask_init_kernel<<<blocks, 256, 0, st>>>(mask, W, P.E, bc);
+          SPAI_CUDA(cudaGetLastError()); ++launches;
+          if (T > 0) {
+            constexpr int U = 4;
+            const int64_t chunks_t = ceil_div(T, 256 * U);
+            const int64_t nblk = chunks_t * bc;
+            if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
+            k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
+                act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t, row_len_dev);
+            SPAI_CUDA(cudaGetLastError()); ++launches;
+          }
         }
       }
     }
@@ -819,6 +911,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   c->last.launches = launches; c->last.chunks = chunks;
   c->last.algorithmic_bytes = plan.g_bytes_full;     // per fully-kept pattern; callers scale by nnz_m / E
   c->last.compulsory_bytes = (double)B * ((double)W * 4.0 + 8.0);
+  c->last.h2d_bytes = h2d_bytes;
   return SPAI_OK;
 }
 

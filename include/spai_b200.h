@@ -165,6 +165,7 @@ typedef struct spai_timing {
   int32_t chunks;
   double algorithmic_bytes; /* SURVEY.md §8d G summed over the batch            */
   double compulsory_bytes;  /* bytes that must cross HBM for the batch           */
+  double h2d_bytes;         /* host->device bytes actually copied (host entry)   */
 } spai_timing;
 int spai_ctx_enable_timing(spai_ctx* ctx, int enable);
 int spai_ctx_last_timing(const spai_ctx* ctx, spai_timing* out);
