@@ -286,4 +286,107 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
   }
 }
 
+// ---------------------------------------------------------------- solve values
+// ls-mode values of M for ONE trajectory (column 0 of maskT): one warp per row,
+// Householder QR as above but R is kept (diagonal in `beta`, pivot rows in
+// `piv`) and the triangular system is solved by back substitution. Output in
+// EDGE order (slot_edge), 0 for removed / dependent candidates.
+template <typename T>
+__global__ void __launch_bounds__(128)
+k2_ls_solve_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
+                   const int32_t* __restrict__ sptr, const int32_t* __restrict__ slot_edge,
+                   const int32_t* __restrict__ r_q, const int32_t* __restrict__ r_diag, int64_t n,
+                   const uint32_t* __restrict__ maskT, int64_t Bp, T* work, int64_t work_stride,
+                   int32_t* imap, int64_t imap_stride, double* __restrict__ m_val) {
+  using Rec = typename RecOf<T>::type;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int q = r_q[i];
+    const int sp = sptr[i];
+    const int k = sptr[i + 1] - sp;
+    if (q == 0 || k == 0) continue;
+    const int diag = r_diag[i];
+    const int64_t cb = cptr[i], ce = cptr[i + 1];
+    int32_t* cmap = imap + warp * imap_stride;          // [k] slot -> column
+    int32_t* piv = cmap + k;                            // [k] column -> pivot row or -1
+    int kk = 0;
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const int e = e0 + lane;
+      bool kept = false;
+      if (e < k) {
+        const int64_t bit = (int64_t)sp + e;
+        kept = (maskT[(bit >> 5) * Bp] >> (bit & 31)) & 1u;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, kept);
+      if (e < k) cmap[e] = kept ? kk + __popc(bal & ((1u << lane) - 1u)) : -1;
+      kk += __popc(bal);
+    }
+    T* A = work + warp * work_stride;                   // kk columns of q, then y[q], beta[kk], x[kk]
+    T* y = A + (int64_t)kk * q;
+    T* beta_v = y + q;
+    T* x = beta_v + kk;
+    for (int64_t t = lane; t < (int64_t)kk * q + q + 2 * kk; t += 32) A[t] = T(0);
+    __syncwarp();
+    for (int64_t c = cb + lane; c < ce; c += 32) {
+      const Rec r = recs[c];
+      const int col = cmap[rec_e(r.flags)];
+      if (col >= 0) A[(int64_t)col * q + rec_s(r.flags)] = rec_a(r);
+    }
+    if (lane == 0 && diag >= 0) y[diag] = T(1);
+    __syncwarp();
+    int p = 0;
+    for (int j = 0; j < kk; ++j) {
+      T* aj = A + (int64_t)j * q;
+      T full = T(0), sig = T(0);
+      for (int r = lane; r < q; r += 32) {
+        const T v = aj[r];
+        full = fma(v, v, full);
+        if (r >= p) sig = fma(v, v, sig);
+      }
+      full = k2_wsum(full);
+      sig = k2_wsum(sig);
+      if (p >= q || !(sig > full * K2Tol<T>::v)) {
+        if (lane == 0) piv[j] = -1;
+        continue;
+      }
+      const T alp = aj[p];
+      const T nrm = sqrt(sig);
+      const T beta = (alp >= T(0)) ? -nrm : nrm;
+      const T inv = T(1) / (sig - alp * beta);
+      __syncwarp();
+      if (lane == 0) { aj[p] = alp - beta; beta_v[j] = beta; piv[j] = p; }
+      __syncwarp();
+      for (int c = j + 1; c <= kk; ++c) {
+        T* ac = A + (int64_t)c * q;
+        T dot = T(0);
+        for (int r = p + lane; r < q; r += 32) dot = fma(aj[r], ac[r], dot);
+        dot = k2_wsum(dot);
+        const T f = dot * inv;
+        for (int r = p + lane; r < q; r += 32) ac[r] = fma(-f, aj[r], ac[r]);
+      }
+      __syncwarp();
+      ++p;
+    }
+    __syncwarp();
+    // back substitution over the active columns (R[piv[j]][c] lives in A[c][piv[j]])
+    for (int j = kk - 1; j >= 0; --j) {
+      const int pj = piv[j];
+      if (pj < 0) continue;                    // uniform: piv is read by all lanes
+      T acc = T(0);
+      for (int c = j + 1 + lane; c < kk; c += 32)
+        if (piv[c] >= 0) acc = fma(A[(int64_t)c * q + pj], x[c], acc);
+      acc = k2_wsum(acc);
+      if (lane == 0) x[j] = (y[pj] - acc) / beta_v[j];
+      __syncwarp();
+    }
+    for (int e = lane; e < k; e += 32) {
+      const int col = cmap[e];
+      if (col >= 0) m_val[slot_edge[sp + e]] = (double)x[col];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace spai

@@ -973,9 +973,54 @@ int spai_row_index_sets(spai_ctx* c, int64_t row, int64_t* num_j, int64_t* j_hos
 
 int spai_ls_solve_values_host(spai_ctx* c, const int64_t* actions, int64_t T, int dtype, double* m_val,
                               void* stream) {
-  (void)c; (void)actions; (void)T; (void)dtype; (void)m_val; (void)stream;
-  set_error("spai_ls_solve_values_host: not implemented yet");
-  return SPAI_ERR_UNSUPPORTED;
+  if (!c || !m_val || T < 0 || (T && !actions) || (dtype != SPAI_F32 && dtype != SPAI_F64)) {
+    set_error("spai_ls_solve_values_host: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  DeviceGuard guard(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SPAI_TRY(ensure_plan(c, dtype, true, st));
+  const Plan& plan = c->plan[dtype];
+  const Pattern& P = c->P;
+  const int64_t W = std::max<int64_t>(P.words(), 1), Bp = 32;
+  Arena tmp;
+  int64_t* act_dev = nullptr;
+  uint32_t *mask = nullptr, *maskT = nullptr;
+  double* out = nullptr;
+  SPAI_TRY(tmp.alloc(&act_dev, T));
+  SPAI_TRY(tmp.alloc(&mask, W));
+  SPAI_TRY(tmp.alloc(&maskT, W * Bp));
+  SPAI_TRY(tmp.alloc(&out, P.E));
+  SPAI_CUDA(cudaMemsetAsync(out, 0, (size_t)std::max<int64_t>(P.E, 1) * 8, st));
+  if (T) SPAI_CUDA(cudaMemcpyAsync(act_dev, actions, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+  if (P.E > 0) {
+    k0_mask_init_kernel<<<(unsigned)std::min<int64_t>(ceil_div(W, 256), 65535), 256, 0, st>>>(mask, W, P.E, 1);
+    if (T) k0_mask_clear_kernel<4><<<(unsigned)ceil_div(T, 1024), 256, 0, st>>>(
+        act_dev, 1, T, T, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, ceil_div(T, 1024), nullptr);
+    k0_transpose_kernel<<<dim3((unsigned)ceil_div(W, 32), 1), 256, 0, st>>>(mask, 1, W, maskT, Bp);
+    SPAI_CUDA(cudaGetLastError());
+    const int64_t warps = (int64_t)c->sm_count * 16;
+    const int64_t kmax = P.max_k, qmax = plan.max_q;
+    const int64_t wstride = qmax * (kmax + 1) + 2 * kmax + 8;
+    const unsigned blocks = (unsigned)(warps / 4);
+    int32_t* imap = nullptr;
+    SPAI_TRY(tmp.alloc(&imap, warps * 2 * std::max<int64_t>(kmax, 1)));
+    if (dtype == SPAI_F32) {
+      float* work = nullptr;
+      SPAI_TRY(tmp.alloc(&work, warps * wstride));
+      k2_ls_solve_kernel<float><<<blocks, 128, 0, st>>>(reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr,
+          P.sptr, P.slot_edge, plan.r_q, plan.r_diag, P.n, maskT, Bp, work, wstride, imap, 2 * kmax, out);
+    } else {
+      double* work = nullptr;
+      SPAI_TRY(tmp.alloc(&work, warps * wstride));
+      k2_ls_solve_kernel<double><<<blocks, 128, 0, st>>>(reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr,
+          P.sptr, P.slot_edge, plan.r_q, plan.r_diag, P.n, maskT, Bp, work, wstride, imap, 2 * kmax, out);
+    }
+    SPAI_CUDA(cudaGetLastError());
+  }
+  SPAI_CUDA(cudaMemcpyAsync(m_val, out, (size_t)P.E * 8, cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaStreamSynchronize(st));
+  return SPAI_OK;
 }
 
 int spai_residual_pair_host(int device, int64_t n, int64_t m_nnz, const int64_t* m_row, const int64_t* m_col,

@@ -193,6 +193,16 @@ class SpaiContext:
               "spai_row_index_sets")
         return j, i
 
+    def ls_solve_values(self, actions_row, dtype: torch.dtype = torch.float64) -> np.ndarray:
+        """Values of M re-solved (ls mode) on the pattern of ONE trajectory, float64[E]
+        in the caller's edge order; 0 for removed edges."""
+        acts = np.ascontiguousarray(np.asarray(actions_row, dtype=np.int64).ravel())
+        out = np.zeros(self.num_edges, dtype=np.float64)
+        check(self._lib.spai_ls_solve_values_host(self._h, _ptr(acts), acts.size,
+                                                  F32 if dtype == torch.float32 else F64, _ptr(out),
+                                                  self._stream()), "spai_ls_solve_values_host")
+        return out
+
     def sample_step(self, logits, taken, uniforms, done, action, prob):
         """In-place masked categorical step on CUDA tensors (include/spai_b200.h)."""
         a = logits.shape[-1]

@@ -234,3 +234,42 @@ def test_drop_in_env_matches_reference_outputs(golden):
     assert env.mask([0, 1]).shape == (2, env.num_actions)
     with pytest.raises(ValueError):
         env.create_mask_from_sparse_matrix(torch.eye(3))
+
+
+@pytest.mark.parametrize("name", ["convdiff16", "uncoalesced40", "poisson10"])
+def test_ls_solve_values_reproduce_the_ls_residual(name):
+    """spai_ls_solve_values_host: the re-solved M, used as explicit values
+    (copy semantics), gives the ls residual; rows agree with LAPACK."""
+    import conftest
+    g = conftest.load_golden(name)
+    ctx = _ctx_from_golden(g)
+    n = int(g["n"])
+    a64 = _a_csr(g, np.float64)
+    b = min(3, g["actions"].shape[0] - 1)
+    acts = g["actions"][b]
+    vals = ctx.ls_solve_values(acts, torch.float64)
+    kept = orc.kept_edge_mask(g["edge_row"].size, acts)
+    assert np.all(vals[~kept] == 0.0)
+    m = orc.build_pattern_matrix(n, g["edge_row"], g["edge_col"], vals, kept, dtype=np.float64)
+    res_from_values = orc.residual_copy(m, a64, dtype=np.float64)
+    ls = ctx.reward_batch(torch.from_numpy(acts[None, :]).cuda(), 0.5, "ls", torch.float64)
+    assert res_from_values == pytest.approx(float(ls["residual"][0]), rel=1e-9, abs=1e-9)
+    # row-wise against LAPACK where the row problem has full column rank
+    pat = orc.build_pattern_matrix(n, g["edge_row"], g["edge_col"], np.ones(g["edge_row"].size), kept, np.float64)
+    mm = m.tocsr()
+    checked = 0
+    for i in range(0, n, max(1, n // 25)):
+        j = np.unique(pat.indices[pat.indptr[i]:pat.indptr[i + 1]])
+        if j.size == 0:
+            continue
+        sub = a64[j, :]
+        iset = np.unique(sub.indices)
+        hat = np.asarray(sub[:, iset].todense()).T
+        if np.linalg.matrix_rank(hat) < j.size:
+            continue
+        _, sol = orc.ls_row_residual2(a64, i, j, return_m=True)
+        got = np.asarray(mm[i, j].todense()).ravel()
+        np.testing.assert_allclose(got, sol, rtol=1e-8, atol=1e-10)
+        checked += 1
+    assert checked > 0
+    ctx.close()
