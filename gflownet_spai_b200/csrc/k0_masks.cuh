@@ -90,8 +90,16 @@ k0_mask_build_smem_kernel(const int64_t* __restrict__ actions, int64_t B, int64_
   if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
     const longlong2* row2 = reinterpret_cast<const longlong2*>(row);
     const int64_t T2 = T >> 1;
-#pragma unroll 4
-    for (int64_t t = tid; t < T2; t += K0S_THREADS) {
+    constexpr int LD = 8;                 // independent 16-byte loads in flight per thread
+    int64_t t = tid;
+    for (; t + (int64_t)(LD - 1) * K0S_THREADS < T2; t += (int64_t)LD * K0S_THREADS) {
+      longlong2 v[LD];
+#pragma unroll
+      for (int u = 0; u < LD; ++u) v[u] = __ldcs(row2 + t + (int64_t)u * K0S_THREADS);
+#pragma unroll
+      for (int u = 0; u < LD; ++u) { clear(v[u].x); clear(v[u].y); }
+    }
+    for (; t < T2; t += K0S_THREADS) {
       const longlong2 v = __ldcs(row2 + t);
       clear(v.x);
       clear(v.y);

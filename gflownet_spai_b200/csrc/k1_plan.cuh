@@ -87,7 +87,7 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
         const int64_t pos = c0 + rank;
         c_col[pos] = x;
         const uint32_t ebit = (k <= 32) ? (1u << e) : 0u;
-        const uint32_t flags = (uint32_t)e << 2;     // segment fields filled in pass 2
+        const uint32_t flags = (uint32_t)e;          // segment fields filled in pass 2
         if constexpr (sizeof(T) == 4) {
           Rec32 r;
           r.ebit = ebit; r.flags = flags; r.w = m * av; r.a = av;
@@ -114,7 +114,7 @@ k1_fill_kernel(int64_t n, const int32_t* __restrict__ sptr, const int32_t* __res
       const unsigned hb = __ballot_sync(full, head);
       const int s = sbase + __popc(hb & (0xffffffffu >> (31 - lane))) - 1;
       if (valid) {
-        uint32_t fl = ((uint32_t)s << 16) | ((next != x) ? F_END : 0u) |
+        uint32_t fl = ((uint32_t)s << 14) | ((next != x) ? F_END : 0u) |
                       ((next != x && next == (int)i) ? F_NEXT_DIAG : 0u);
         if constexpr (sizeof(T) == 4) {
           rc32[c0 + p].flags = __ldcg(&rc32[c0 + p].flags) | fl;

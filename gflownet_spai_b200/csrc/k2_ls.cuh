@@ -44,26 +44,37 @@ template <typename T> struct K2Tol;
 template <> struct K2Tol<float>  { static constexpr float  v = 1e-10f; };   // (~85 eps)^2
 template <> struct K2Tol<double> { static constexpr double v = 1e-26;  };   // (~450 eps)^2
 
+__device__ __forceinline__ float k2_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double k2_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float k2_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double k2_rcp(double x) { return __drcp_rn(x); }
+
 // One Householder step on column E of the lane-distributed tile. E is a
 // template parameter so that every register-array index is a compile-time
-// constant (a runtime column loop would demote `a` to local memory).
+// constant (a runtime column loop would demote `a` to local memory). `kkw` is
+// the largest number of kept columns among the problems of this warp: the kept
+// columns are compacted to the front when the tile is loaded, so steps and
+// trailing columns >= kkw are all-zero for every lane and are skipped with
+// warp-uniform branches.
 template <typename T, int KMAX, int G, int QL, int E>
-__device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p,
-                                        const T* __restrict__ coln2, int lg) {
+__device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p, T (&cn2)[KMAX],
+                                        int lg, int kkw) {
+  if (E >= kkw) return;
   T sig = T(0), alp = T(0);
 #pragma unroll
   for (int t = 0; t < QL; ++t) {
     const int r = t * G + lg;
     const T v = (r >= p) ? a[t][E] : T(0);
     sig = fma(v, v, sig);
-    alp += (r == p) ? v : T(0);
+    alp = (r == p) ? v : alp;
   }
   sig = k2_gsum<G>(sig);
   alp = k2_gsum<G>(alp);
-  const bool act = sig > coln2[E] * K2Tol<T>::v;
-  const T nrm = sqrt(sig);
+  const bool act = sig > cn2[E] * K2Tol<T>::v;
+  const T sg = act ? sig : T(1);
+  const T nrm = sg * k2_rsqrt(sg);
   const T beta = (alp >= T(0)) ? -nrm : nrm;
-  const T inv = act ? T(1) / (sig - alp * beta) : T(0);
+  const T inv = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
   T vt[QL];
 #pragma unroll
   for (int t = 0; t < QL; ++t) {
@@ -72,13 +83,15 @@ __device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p,
   }
 #pragma unroll
   for (int c = E + 1; c < KMAX; ++c) {
-    T dot = T(0);
+    if (c < kkw) {
+      T dot = T(0);
 #pragma unroll
-    for (int t = 0; t < QL; ++t) dot = fma(vt[t], a[t][c], dot);
-    dot = k2_gsum<G>(dot);
-    const T f = dot * inv;
+      for (int t = 0; t < QL; ++t) dot = fma(vt[t], a[t][c], dot);
+      dot = k2_gsum<G>(dot);
+      const T f = dot * inv;
 #pragma unroll
-    for (int t = 0; t < QL; ++t) a[t][c] = fma(-f, vt[t], a[t][c]);
+      for (int t = 0; t < QL; ++t) a[t][c] = fma(-f, vt[t], a[t][c]);
+    }
   }
   {
     T dot = T(0);
@@ -93,10 +106,9 @@ __device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p,
 }
 
 template <typename T, int KMAX, int G, int QL, int... Es>
-__device__ __forceinline__ void k2_all_steps(T (&a)[QL][KMAX], T (&y)[QL], int& p,
-                                             const T* __restrict__ coln2, int lg,
-                                             std::integer_sequence<int, Es...>) {
-  (k2_step<T, KMAX, G, QL, Es>(a, y, p, coln2, lg), ...);
+__device__ __forceinline__ void k2_all_steps(T (&a)[QL][KMAX], T (&y)[QL], int& p, T (&cn2)[KMAX],
+                                             int lg, int kkw, std::integer_sequence<int, Es...>) {
+  (k2_step<T, KMAX, G, QL, Es>(a, y, p, cn2, lg, kkw), ...);
 }
 
 constexpr int K2_NW = 4;          // warps per block
@@ -161,17 +173,24 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
       const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
       const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
 
+      // compact the kept columns to the front: column c' <- c'-th kept slot
       T a[QL][KMAX];
       T y[QL];
+      T cn2[KMAX];
+      uint32_t mm = m;
 #pragma unroll
-      for (int t = 0; t < QL; ++t) {
-        const int r = t * G + lg;
+      for (int cc = 0; cc < KMAX; ++cc) {
+        const int e = __ffs(mm) - 1;           // -1 once the kept slots are exhausted
+        mm &= mm - 1u;
+        cn2[cc] = (e >= 0) ? coln2[e] : T(0);
 #pragma unroll
-        for (int e = 0; e < KMAX; ++e) a[t][e] = ((m >> e) & 1u) ? tile[r * KMAX + e] : T(0);
-        y[t] = (r == diag) ? T(1) : T(0);
+        for (int t = 0; t < QL; ++t) a[t][cc] = (e >= 0) ? tile[(t * G + lg) * KMAX + e] : T(0);
       }
+#pragma unroll
+      for (int t = 0; t < QL; ++t) y[t] = ((t * G + lg) == diag) ? T(1) : T(0);
+      const int kkw = __reduce_max_sync(0xffffffffu, __popc(m));
       int p = 0;
-      k2_all_steps<T, KMAX, G, QL>(a, y, p, coln2, lg, std::make_integer_sequence<int, KMAX>{});
+      k2_all_steps<T, KMAX, G, QL>(a, y, p, cn2, lg, kkw, std::make_integer_sequence<int, KMAX>{});
       T r2 = T(0);
 #pragma unroll
       for (int t = 0; t < QL; ++t) {

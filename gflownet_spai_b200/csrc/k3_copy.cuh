@@ -136,17 +136,16 @@ __device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt,
     acc[j] = a0;
   }
   int c = 0;
-  Rec nx = rp[0];
   while (c < cnt) {
-    Rec r;
+    int fl;
     do {
-      r = nx;
-      nx = rp[++c];
+      const Rec r = rp[c++];
+      fl = (int)r.flags;
       const T w = rec_w(r);
 #pragma unroll
       for (int j = 0; j < NT; ++j) k3_cond_add(acc[j], m[j], r.ebit, w);
-    } while (!(r.flags & F_END));
-    const T nxt = (r.flags & F_NEXT_DIAG) ? T(-1) : T(0);
+    } while (fl >= 0);                                   // END is the sign bit
+    const T nxt = ((uint32_t)fl & F_NEXT_DIAG) ? T(-1) : T(0);
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       rs[j] = fma(acc[j], acc[j], rs[j]);

@@ -38,18 +38,18 @@ void set_error(const char* fmt, ...);
 // the row's candidate list reaches output column x. Records of a row are sorted
 // by (x, e); records with the same x form one output segment (one entry of the
 // row of M*A). 16 bytes, so a run of records is a legal cp.async.bulk source.
-//   flags: bit0 END  last record of its output segment
-//          bit1 NEXT_DIAG (END records only) the FOLLOWING segment's column is
-//               the row index, i.e. the entry that carries the "-1" of "-I"
-//          bits 2..15  e  slot index inside the row (< 16384)
-//          bits 16..31 s  output segment index inside the row (< 65536)
-constexpr uint32_t F_END = 1u;
-constexpr uint32_t F_NEXT_DIAG = 2u;
+//   flags: bit31 END  last record of its output segment (sign bit: one ISETP)
+//          bit30 NEXT_DIAG (END records only) the FOLLOWING segment's column is
+//                the row index, i.e. the entry that carries the "-1" of "-I"
+//          bits 14..29 s  output segment index inside the row (< 65536)
+//          bits 0..13  e  slot index inside the row (< 16384)
+constexpr uint32_t F_END = 0x80000000u;
+constexpr uint32_t F_NEXT_DIAG = 0x40000000u;
 constexpr int MAX_ROW_SLOTS = 16384;
 constexpr int MAX_ROW_UNION = 65536;
 
-__host__ __device__ __forceinline__ uint32_t rec_e(uint32_t flags) { return (flags >> 2) & 0x3fffu; }
-__host__ __device__ __forceinline__ uint32_t rec_s(uint32_t flags) { return flags >> 16; }
+__host__ __device__ __forceinline__ uint32_t rec_e(uint32_t flags) { return flags & 0x3fffu; }
+__host__ __device__ __forceinline__ uint32_t rec_s(uint32_t flags) { return (flags >> 14) & 0xffffu; }
 
 struct alignas(16) Rec32 {
   uint32_t ebit;   // 1u << e when the row has <= 32 slots, else 0
