@@ -209,6 +209,168 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
   }
 }
 
+// ---------------------------------------------------------------- column-per-lane kernel
+// For k > 8 the row-distributed layout above is bound by warp shuffles (one
+// xor-butterfly per trailing column and step: the shuffle unit retires one warp
+// instruction per SM and clock). Here a problem owns W lanes (W = 16 or 32) and
+// lane c holds COLUMN c of the compacted tile in registers (QMAX rows, static
+// indices), so v^T a_c and the update are lane-local; the reflector v of step E
+// is published by its owner lane through a per-problem shared-memory buffer and
+// read back as warp-broadcast LDS.128. The right-hand side e_i lives in shared
+// memory with its rows dealt over the W lanes (one butterfly per step). Full
+// column rank is assumed (pivot row == step index: every index is static);
+// a tile that turns out rank-deficient is pushed to `fail_pairs` and redone by
+// the generic kernel.
+template <typename T, int W, int QMAX, int E>
+__device__ __forceinline__ void k2c_step(T (&a)[QMAX], T cn, T* __restrict__ vb, T* __restrict__ yb,
+                                         int lc, int kk, int kkw, bool& bad) {
+  if (E >= kkw) return;                                   // warp-uniform
+  if constexpr (E < QMAX) {
+    T sg4[4] = {T(0), T(0), T(0), T(0)};                  // 4 chains: FMA latency, not throughput, binds at low occupancy
+#pragma unroll
+    for (int r = E; r < QMAX; ++r) sg4[(r - E) & 3] = fma(a[r], a[r], sg4[(r - E) & 3]);
+    const T sig = (sg4[0] + sg4[1]) + (sg4[2] + sg4[3]);
+    const T alp = a[E];
+    const bool act = sig > cn * K2Tol<T>::v;
+    const T sg = act ? sig : T(1);
+    const T nrm = sg * k2_rsqrt(sg);
+    const T beta = (alp >= T(0)) ? -nrm : nrm;
+    const T inv_o = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
+    if (lc == E) {                                        // owner publishes v (rows >= E)
+      vb[E] = alp - beta;
+#pragma unroll
+      for (int r = E + 1; r < QMAX; ++r) vb[r] = a[r];
+    }
+    const T inv = __shfl_sync(0xffffffffu, inv_o, E, W);
+    const bool live = E < kk;
+    bad |= live && (inv == T(0));
+    __syncwarp();
+    // trailing columns (lanes > E): dot, update
+    T dt4[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int r = E; r < QMAX; ++r) dt4[(r - E) & 3] = fma(vb[r], a[r], dt4[(r - E) & 3]);
+    const T dot = (dt4[0] + dt4[1]) + (dt4[2] + dt4[3]);
+    const T f = (lc > E) ? dot * inv : T(0);
+#pragma unroll
+    for (int r = E; r < QMAX; ++r) a[r] = fma(-f, vb[r], a[r]);
+    // right-hand side: rows dealt over the W lanes
+    T py = T(0);
+#pragma unroll
+    for (int r = lc; r < QMAX; r += W) py += (r >= E) ? vb[r] * yb[r] : T(0);
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+    const T fy = py * inv;
+#pragma unroll
+    for (int r = lc; r < QMAX; r += W)
+      if (r >= E) yb[r] = fma(-fy, vb[r], yb[r]);
+    __syncwarp();
+  }
+}
+
+template <typename T, int W, int QMAX, int... Es>
+__device__ __forceinline__ void k2c_all_steps(T (&a)[QMAX], T cn, T* vb, T* yb, int lc, int kk, int kkw,
+                                              bool& bad, std::integer_sequence<int, Es...>) {
+  (k2c_step<T, W, QMAX, Es>(a, cn, vb, yb, lc, kk, kkw, bad), ...);
+}
+
+template <typename T, int W, int QMAX>
+__global__ void __launch_bounds__(K2_NW * 32)
+k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
+              const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
+              const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
+              int64_t Bp, int64_t B, int ntg, double* __restrict__ partial, int2* __restrict__ fail_pairs,
+              unsigned int* __restrict__ fail_count, unsigned int fail_cap) {
+  using Rec = typename RecOf<T>::type;
+  constexpr int NP = 32 / W;                       // problems per warp
+  constexpr int NTHREADS = K2_NW * 32;
+  constexpr int GROUPS = K2_NW * NP;
+  __shared__ __align__(16) T tile[QMAX * W];       // [row][slot]
+  __shared__ T coln2[W];
+  __shared__ __align__(16) T vbuf[GROUPS][QMAX];
+  __shared__ __align__(16) T ybuf[GROUPS][QMAX];
+  __shared__ double totsm[K2_MAX_NTG * GROUPS];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int pr = lane / W, lc = lane % W;
+  const int gid = warp * NP + pr;
+  const int64_t bbase = (int64_t)blockIdx.y * ((int64_t)GROUPS * ntg);
+  T* vb = vbuf[gid];
+  T* yb = ybuf[gid];
+
+  for (int x = tid; x < K2_MAX_NTG * GROUPS; x += NTHREADS) totsm[x] = 0.0;
+
+  const int64_t ri0 = nrows * blockIdx.x / gridDim.x;
+  const int64_t ri1 = nrows * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t ri = ri0; ri < ri1; ++ri) {
+    const int i = rows[ri];
+    const int64_t cb = cptr[i], ce = cptr[i + 1];
+    const int sp = sptr[i];
+    const int k = sptr[i + 1] - sp;
+    const int diag = r_diag[i];
+    __syncthreads();
+    for (int x = tid; x < QMAX * W; x += NTHREADS) tile[x] = T(0);
+    __syncthreads();
+    for (int64_t c = cb + tid; c < ce; c += NTHREADS) {
+      const Rec r = recs[c];
+      tile[rec_s(r.flags) * W + rec_e(r.flags)] = rec_a(r);
+    }
+    __syncthreads();
+    if (tid < W) {
+      T s = T(0);
+      for (int q = 0; q < QMAX; ++q) { const T v = tile[q * W + tid]; s = fma(v, v, s); }
+      coln2[tid] = s;
+    }
+    __syncthreads();
+
+    const int64_t w0 = sp >> 5;
+    const int sh = sp & 31;
+    const bool two = sh + k > 32;
+    const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+
+#pragma unroll 1
+    for (int j = 0; j < ntg; ++j) {
+      const int64_t breal = bbase + (int64_t)j * GROUPS + gid;
+      const int64_t b = (breal < Bp) ? breal : 0;
+      const uint32_t lo = maskT[w0 * Bp + b];
+      const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
+      const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
+      const int kk = __popc(m);
+      const int kkw = __reduce_max_sync(0xffffffffu, kk);
+      const int e = (lc < kk) ? (int)__fns(m, 0, lc + 1) : -1;       // my column = lc-th kept slot
+      T a[QMAX];
+#pragma unroll
+      for (int r = 0; r < QMAX; ++r) a[r] = (e >= 0) ? tile[r * W + e] : T(0);
+      const T cn = (e >= 0) ? coln2[e] : T(0);
+#pragma unroll
+      for (int r = lc; r < QMAX; r += W) yb[r] = (r == diag) ? T(1) : T(0);
+      __syncwarp();
+      bool bad = false;
+      k2c_all_steps<T, W, QMAX>(a, cn, vb, yb, lc, kk, kkw, bad, std::make_integer_sequence<int, W>{});
+      T r2 = T(0);
+#pragma unroll
+      for (int r = lc; r < QMAX; r += W) r2 += (r >= kk) ? yb[r] * yb[r] : T(0);
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      __syncwarp();
+      if (lc == 0) {
+        if (bad && breal < B) {
+          const unsigned int slot = atomicAdd(fail_count, 1u);
+          if (slot < fail_cap) fail_pairs[slot] = make_int2(i, (int)breal);
+          r2 = T(0);                                       // redone by the generic kernel
+        }
+        totsm[j * GROUPS + gid] += (double)r2;
+      }
+    }
+  }
+  __syncthreads();
+  for (int x = tid; x < ntg * GROUPS; x += NTHREADS) {
+    const int j = x / GROUPS, g = x % GROUPS;
+    const int64_t b = bbase + (int64_t)j * GROUPS + g;
+    if (b < Bp) partial[(int64_t)blockIdx.x * Bp + b] = totsm[x];
+  }
+}
+
 // ---------------------------------------------------------------- generic path
 // One warp per (row, trajectory). Scratch per warp: kk columns of q entries
 // (column-major) + y[q]. Any k (kept bits fetched word by word) and any q.
@@ -227,17 +389,22 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
                      const int32_t* __restrict__ rows, int64_t nrows,
                      const uint32_t* __restrict__ maskT, int64_t Bp, int64_t B, T* work,
                      int64_t work_stride, int32_t* colmap, int64_t colmap_stride,
-                     double* __restrict__ res2) {
+                     double* __restrict__ res2, const int2* __restrict__ pairs,
+                     const unsigned int* __restrict__ npairs, unsigned int pair_cap) {
   using Rec = typename RecOf<T>::type;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   T* A = work + warp * work_stride;
   int32_t* cmap = colmap + warp * colmap_stride;
-  const int64_t items = nrows * B;
+  // two modes: every (row of `rows`) x (trajectory), or the (row, trajectory)
+  // pairs a register kernel could not finish (rank-deficient tiles)
+  const int64_t items = pairs ? (int64_t)min(*npairs, pair_cap) : nrows * B;
   for (int64_t it = warp; it < items; it += nwarps) {
-    const int64_t ri = it / B, b = it % B;
-    const int i = rows[ri];
+    int64_t b;
+    int i;
+    if (pairs) { i = pairs[it].x; b = pairs[it].y; }
+    else { i = rows[it / B]; b = it % B; }
     const int q = r_q[i];
     const int sp = sptr[i];
     const int k = sptr[i + 1] - sp;

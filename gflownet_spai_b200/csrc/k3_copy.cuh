@@ -274,10 +274,13 @@ __global__ void k3_finalize_kernel(const double* __restrict__ partial, int npart
                                    double rows_missing_diag, const long long* __restrict__ nnz,
                                    double n, double res0, double flops0, double alpha,
                                    double* __restrict__ reward, double* __restrict__ residual,
-                                   long long* __restrict__ nnz_out) {
+                                   long long* __restrict__ nnz_out,
+                                   const unsigned int* __restrict__ fail_count, unsigned int fail_cap) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double s = rows_missing_diag;
+  // more rank-deficient tiles than the hand-over list can hold: fail loudly (NaN)
+  if (fail_count && *fail_count > fail_cap) s = __longlong_as_double(0x7ff8000000000000LL);
   for (int g = 0; g < nparts; ++g) s += partial[(int64_t)g * Bp + b];
   if (res2_extra) s += res2_extra[b];
   const double res = sqrt(s);

@@ -176,18 +176,22 @@ static int upload_csr(Arena& ar, const HostCsr& h, int64_t n, int64_t stored, Cs
   return SPAI_OK;
 }
 
-// ls register-kernel classes: {KMAX, G, QL, available for f64}
-struct LsClass { int kmax, g, ql; bool f64; };
+// ls register-kernel classes.
+//   kind 0: row-distributed tile (k2_ls_kernel<T,KMAX,G,QL>), rows up to G*QL
+//   kind 1: column-per-lane tile (k2c_ls_kernel<T,W,QMAX>), W = KMAX lanes per problem
+struct LsClass { int kind, kmax, g, ql; };
 static const LsClass kLsClasses[LS_NCLASS - 1] = {
-    {8, 4, 5, true}, {8, 8, 5, true}, {16, 16, 3, true}, {16, 32, 3, true},
-    {32, 32, 2, true}, {32, 32, 4, false}, {0, 0, 0, false}};
+    {0, 8, 4, 5}, {0, 8, 8, 5}, {1, 16, 16, 52}, {1, 16, 16, 64},
+    {1, 32, 32, 52}, {1, 32, 32, 64}, {0, 0, 0, 0}};
+static inline int ls_class_rows_max(const LsClass& L) { return L.kind == 0 ? L.g * L.ql : L.ql; }
+static inline int ls_class_lanes(const LsClass& L) { return L.g; }
 
-static int classify_row(int k, int q, int dtype) {
+static int classify_row(int k, int q, bool has_dup) {
   for (int c = 0; c < LS_NCLASS - 1; ++c) {
     const LsClass& L = kLsClasses[c];
     if (L.kmax == 0) continue;
-    if (dtype == SPAI_F64 && !L.f64) continue;
-    if (k <= L.kmax && q <= L.g * L.ql) return c;
+    if (L.kind == 1 && has_dup) continue;        // column kernel assumes full column rank
+    if (k <= L.kmax && q <= ls_class_rows_max(L)) return c;
   }
   return LS_GENERIC;
 }
@@ -256,7 +260,13 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
   SPAI_TRY(ar.upload(&plan.tile_row, tiles));
 
   std::vector<int32_t> cls[LS_NCLASS];
-  plan.rows_missing_diag = 0; plan.max_q = 0;
+  std::vector<char> row_dup(n, 0);
+  for (size_t g = 0; g < hp.dup_start.size(); ++g) {
+    const int32_t s0 = hp.dup_start[g];
+    const int64_t row = std::upper_bound(hp.sptr.begin(), hp.sptr.end(), s0) - hp.sptr.begin() - 1;
+    row_dup[row] = 1;
+  }
+  plan.rows_missing_diag = 0; plan.max_q = 0; plan.max_k = P.max_k;
   plan.generic_max_q = plan.generic_max_k = 0;
   const double w = (dtype == SPAI_F32) ? 4.0 : 8.0;
   double g = 0.0;
@@ -268,7 +278,7 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
     plan.max_q = std::max(plan.max_q, q);
     g += k * (4.0 + w + 8.0) + (double)hc[i] * (4.0 + w);
     if (q == 0) continue;
-    const int c = classify_row(k, q, dtype);
+    const int c = classify_row(k, q, row_dup[i] != 0);
     cls[c].push_back((int32_t)i);
     if (c == LS_GENERIC) {
       plan.generic_max_q = std::max<int64_t>(plan.generic_max_q, q);
@@ -312,12 +322,15 @@ struct Carver {
 };
 static inline int64_t padded(int64_t bytes) { return round_up(bytes, 256) + 256; }
 
+constexpr unsigned int LS_FAIL_CAP = 1u << 18;   // (row, trajectory) tiles redone by the generic kernel
+
 struct EvalShape {       // launch geometry of one reward evaluation over Bc trajectories
   int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
   int nt = 1, gx = 1, gy = 1;                       // copy kernel
   int ls_gx[LS_NCLASS] = {}, ls_gy[LS_NCLASS] = {}, ls_ntg[LS_NCLASS] = {};
   int parts = 1;
   int64_t generic_work = 0, generic_cmap = 0, generic_warps = 0;
+  bool has_column_class = false;      // column-per-lane kernels may hand tiles to the generic kernel
 };
 
 static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, int sm_count) {
@@ -338,17 +351,20 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
       if (!plan.class_count[c]) continue;
       const LsClass& L = kLsClasses[c];
-      const int groups = K2_NW * (32 / L.g);
+      const int groups = K2_NW * (32 / ls_class_lanes(L));
+      if (L.kind == 1) s.has_column_class = true;
       s.ls_ntg[c] = (int)std::min<int64_t>(K2_MAX_NTG, ceil_div(Bp, groups));
       s.ls_gy[c] = (int)ceil_div(Bp, (int64_t)groups * s.ls_ntg[c]);
       const int target = sm_count * 12;
       s.ls_gx[c] = (int)std::max<int64_t>(1, std::min<int64_t>(plan.class_count[c], std::max(1, target / s.ls_gy[c])));
       s.parts += s.ls_gx[c];
     }
-    if (plan.class_count[LS_GENERIC]) {
+    if (plan.class_count[LS_GENERIC] || s.has_column_class) {
       s.generic_warps = (int64_t)sm_count * 16;
-      s.generic_work = plan.generic_max_q * (plan.generic_max_k + 1);
-      s.generic_cmap = plan.generic_max_k;
+      const int64_t gq = s.has_column_class ? plan.max_q : plan.generic_max_q;
+      const int64_t gk = s.has_column_class ? plan.max_k : plan.generic_max_k;
+      s.generic_work = std::max<int64_t>(gq, 1) * (gk + 1);
+      s.generic_cmap = std::max<int64_t>(gk, 1);
     }
     if (s.parts == 0) s.parts = 1;
   }
@@ -362,8 +378,9 @@ static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int d
               + padded((int64_t)s.parts * Bp * 8)
               + padded(Bp * 8);                // res2 extra
   if (s.generic_warps) {
-    b += padded(s.generic_warps * s.generic_work * (dtype == SPAI_F32 ? 4 : 8));
+    b += padded(s.generic_warps * s.generic_work * 8);
     b += padded(s.generic_warps * s.generic_cmap * 4);
+    b += padded((int64_t)LS_FAIL_CAP * 8) + padded(64);
   }
   (void)plan;
   return b;
@@ -371,31 +388,34 @@ static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int d
 
 template <typename T>
 static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const EvalShape& s,
-                           const uint32_t* maskT, int64_t Bp, double* partial, cudaStream_t st) {
+                           const uint32_t* maskT, int64_t Bp, int64_t Bc, double* partial, int2* fail_pairs,
+                           unsigned int* fail_count, cudaStream_t st) {
   using Rec = typename RecOf<T>::type;
   const Rec* recs = reinterpret_cast<const Rec*>(plan.rec_ls);
   const dim3 grid(s.ls_gx[c], s.ls_gy[c]);
   const dim3 block(K2_NW * 32);
-#define SPAI_LS_CASE(IDX, KMAX, G, QL)                                                         \
+#define SPAI_LS_ROW(IDX, KMAX, G, QL)                                                          \
   case IDX:                                                                                    \
     k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
         plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial);             \
     break;
+#define SPAI_LS_COL(IDX, W, QMAX)                                                              \
+  case IDX:                                                                                    \
+    k2c_ls_kernel<T, W, QMAX><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,     \
+        plan.class_rows[c], plan.class_count[c], maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs, \
+        fail_count, LS_FAIL_CAP);                                                              \
+    break;
   switch (c) {
-    SPAI_LS_CASE(0, 8, 4, 5)
-    SPAI_LS_CASE(1, 8, 8, 5)
-    SPAI_LS_CASE(2, 16, 16, 3)
-    SPAI_LS_CASE(3, 16, 32, 3)
-    SPAI_LS_CASE(4, 32, 32, 2)
-    case 5:
-      if constexpr (sizeof(T) == 4) {
-        k2_ls_kernel<T, 32, 32, 4><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,
-            plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial);
-      }
-      break;
+    SPAI_LS_ROW(0, 8, 4, 5)
+    SPAI_LS_ROW(1, 8, 8, 5)
+    SPAI_LS_COL(2, 16, 52)
+    SPAI_LS_COL(3, 16, 64)
+    SPAI_LS_COL(4, 32, 52)
+    SPAI_LS_COL(5, 32, 64)
     default: set_error("bad ls class %d", c); return SPAI_ERR_INVALID;
   }
-#undef SPAI_LS_CASE
+#undef SPAI_LS_ROW
+#undef SPAI_LS_COL
   SPAI_CUDA(cudaGetLastError());
   return SPAI_OK;
 }
@@ -441,6 +461,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   if (pt && pt->on) cudaEventRecord(pt->ev[2], st);
 
   bool use_extra = false;
+  const unsigned int* fail_count_dev = nullptr;
   int parts = s.parts;
   if (mode == SPAI_MODE_COPY) {
     const dim3 grid(s.gx, s.gy);
@@ -461,43 +482,60 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     SPAI_CUDA(cudaGetLastError()); ++nl;
   } else {
     if (!plan.rec_ls) { set_error("plan was built without ls records"); return SPAI_ERR_INVALID; }
+    int2* fail_pairs = nullptr;
+    unsigned int* fail_count = nullptr;
+    void* gwork = nullptr;
+    int32_t* cmap = nullptr;
+    if (s.generic_warps) {
+      gwork = cv.take<double>(s.generic_warps * s.generic_work);       // sized for fp64, also holds fp32
+      cmap = cv.take<int32_t>(s.generic_warps * s.generic_cmap);
+      fail_pairs = cv.take<int2>(LS_FAIL_CAP);
+      fail_count = cv.take<unsigned int>(16);
+      SPAI_CUDA(cudaMemsetAsync(fail_count, 0, 64, st));
+      SPAI_CUDA(cudaMemsetAsync(res2x, 0, (size_t)Bp * 8, st));
+      use_extra = true;
+      fail_count_dev = fail_count;
+    }
     int off = 0;
     bool any = false;
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
       if (!plan.class_count[c]) continue;
       double* pp = partial + (int64_t)off * Bp;
-      if (dtype == SPAI_F32) SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, pp, st));
-      else SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, pp, st));
+      if (dtype == SPAI_F32)
+        SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st));
+      else
+        SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st));
       off += s.ls_gx[c]; ++nl; any = true;
     }
     if (!any) { SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); parts = 1; }
     else parts = off;
-    if (plan.class_count[LS_GENERIC]) {
-      use_extra = true;
-      SPAI_CUDA(cudaMemsetAsync(res2x, 0, (size_t)Bp * 8, st));
+    if (s.generic_warps) {
       const unsigned blocks = (unsigned)(s.generic_warps / 4);
-      if (dtype == SPAI_F32) {
-        float* work = cv.take<float>(s.generic_warps * s.generic_work);
-        int32_t* cmap = cv.take<int32_t>(s.generic_warps * s.generic_cmap);
-        k2_ls_generic_kernel<float><<<blocks, 128, 0, st>>>(
-            reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
-            plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc, work,
-            s.generic_work, cmap, s.generic_cmap, res2x);
-      } else {
-        double* work = cv.take<double>(s.generic_warps * s.generic_work);
-        int32_t* cmap = cv.take<int32_t>(s.generic_warps * s.generic_cmap);
-        k2_ls_generic_kernel<double><<<blocks, 128, 0, st>>>(
-            reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
-            plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc, work,
-            s.generic_work, cmap, s.generic_cmap, res2x);
+      for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: the rows classified as generic; pass 1: tiles handed over by the column kernels
+        if (pass == 0 && !plan.class_count[LS_GENERIC]) continue;
+        if (pass == 1 && !s.has_column_class) continue;
+        const int2* pairs = pass ? fail_pairs : nullptr;
+        if (dtype == SPAI_F32)
+          k2_ls_generic_kernel<float><<<blocks, 128, 0, st>>>(
+              reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
+              plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
+              reinterpret_cast<float*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
+              LS_FAIL_CAP);
+        else
+          k2_ls_generic_kernel<double><<<blocks, 128, 0, st>>>(
+              reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
+              plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
+              reinterpret_cast<double*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
+              LS_FAIL_CAP);
+        SPAI_CUDA(cudaGetLastError()); ++nl;
       }
-      SPAI_CUDA(cudaGetLastError()); ++nl;
     }
   }
   if (pt && pt->on) cudaEventRecord(pt->ev[3], st);
   k3_finalize_kernel<<<(unsigned)ceil_div(Bc, 256), 256, 0, st>>>(
       partial, parts, Bp, Bc, use_extra ? res2x : nullptr, (double)plan.rows_missing_diag, nnz, n_d,
-      res0, flops0, alpha, reward, residual, reinterpret_cast<long long*>(nnz_out));
+      res0, flops0, alpha, reward, residual, reinterpret_cast<long long*>(nnz_out), fail_count_dev, LS_FAIL_CAP);
   SPAI_CUDA(cudaGetLastError()); ++nl;
   if (launches) *launches += nl;
   return SPAI_OK;

@@ -121,6 +121,7 @@ struct Plan {
   RowHdr* rhdr = nullptr;         // [n]
   int64_t rows_missing_diag = 0;  // rows with r_diag < 0 (each adds 1 to ||.||^2)
   int max_q = 0;
+  int max_k = 0;
   // copy-kernel tiling: tile t = rows [tile_row[t], tile_row[t+1])
   int32_t* tile_row = nullptr;    // [ntiles+1] device
   int ntiles = 0;

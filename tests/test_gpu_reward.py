@@ -273,3 +273,35 @@ def test_ls_solve_values_reproduce_the_ls_residual(name):
         checked += 1
     assert checked > 0
     ctx.close()
+
+
+def test_host_entry_trims_padding_exactly():
+    """spai_reward_batch_host copies only the prefix that still holds ids (rows
+    are scanned back over the -1 padding). -1 in the middle of a row, all-padding
+    rows, rows without padding and a leading dimension > T must all score like
+    the device entry point."""
+    p = synth.make_problem("cfg2", scale=0.25)           # 64 x 64 grid, E = 32 760
+    coo = p.a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data)
+    rng = np.random.default_rng(5)
+    bsz, t = 37, 9000                                    # T >= 4096 -> trimmed path
+    acts = np.full((bsz, t), -1, dtype=np.int64)
+    for b in range(bsz):
+        n_valid = int(rng.integers(0, t))
+        acts[b, :n_valid] = rng.integers(0, p.num_edges, n_valid)
+        holes = rng.integers(0, max(n_valid, 1), 20)
+        acts[b, holes] = -1                              # -1 anywhere is legal and ignored
+    acts[3, :] = -1                                      # nothing removed
+    acts[4, :] = rng.integers(0, p.num_edges, t)         # no padding at all
+    acts[5, -1] = 7                                      # a real id in the very last slot
+    wide = torch.full((bsz, t + 13), -1, dtype=torch.int64)
+    wide[:, :t] = torch.from_numpy(acts)
+    dev = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "copy", torch.float64)
+    for host_in in (torch.from_numpy(acts), wide[:, :t]):            # contiguous and ld > T
+        host = ctx.reward_batch(host_in, 0.5, "copy", torch.float64)
+        assert torch.equal(host["nnz_m"], dev["nnz_m"].cpu())
+        assert torch.equal(host["reward"], dev["reward"].cpu())
+    kept = orc.kept_edge_mask(p.num_edges, acts[5])
+    assert not kept[7] and int(dev["nnz_m"][3]) == p.num_edges
+    ctx.close()
