@@ -221,56 +221,53 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
 // column rank is assumed (pivot row == step index: every index is static);
 // a tile that turns out rank-deficient is pushed to `fail_pairs` and redone by
 // the generic kernel.
-template <typename T, int W, int QMAX, int E>
+// One Householder step; E is a RUNTIME value (the step loop is not unrolled: a
+// fully unrolled 32-step body is ~180 KB of straight-line SASS that every warp
+// streams once per problem — instruction fetch became the bottleneck). Register
+// indices stay static because every row loop runs over all QMAX rows; rows
+// above the pivot are neutralised by zeros in the published reflector.
+template <typename T, int W, int QMAX>
 __device__ __forceinline__ void k2c_step(T (&a)[QMAX], T cn, T* __restrict__ vb, T* __restrict__ yb,
-                                         int lc, int kk, int kkw, bool& bad) {
-  if (E >= kkw) return;                                   // warp-uniform
-  if constexpr (E < QMAX) {
-    T sg4[4] = {T(0), T(0), T(0), T(0)};                  // 4 chains: FMA latency, not throughput, binds at low occupancy
+                                         int lc, int kk, int E, bool& bad) {
+  T sg4[4] = {T(0), T(0), T(0), T(0)};                    // 4 chains: FMA latency binds at low occupancy
+  T alp = T(0);
 #pragma unroll
-    for (int r = E; r < QMAX; ++r) sg4[(r - E) & 3] = fma(a[r], a[r], sg4[(r - E) & 3]);
-    const T sig = (sg4[0] + sg4[1]) + (sg4[2] + sg4[3]);
-    const T alp = a[E];
-    const bool act = sig > cn * K2Tol<T>::v;
-    const T sg = act ? sig : T(1);
-    const T nrm = sg * k2_rsqrt(sg);
-    const T beta = (alp >= T(0)) ? -nrm : nrm;
-    const T inv_o = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
-    if (lc == E) {                                        // owner publishes v (rows >= E)
-      vb[E] = alp - beta;
-#pragma unroll
-      for (int r = E + 1; r < QMAX; ++r) vb[r] = a[r];
-    }
-    const T inv = __shfl_sync(0xffffffffu, inv_o, E, W);
-    const bool live = E < kk;
-    bad |= live && (inv == T(0));
-    __syncwarp();
-    // trailing columns (lanes > E): dot, update
-    T dt4[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-    for (int r = E; r < QMAX; ++r) dt4[(r - E) & 3] = fma(vb[r], a[r], dt4[(r - E) & 3]);
-    const T dot = (dt4[0] + dt4[1]) + (dt4[2] + dt4[3]);
-    const T f = (lc > E) ? dot * inv : T(0);
-#pragma unroll
-    for (int r = E; r < QMAX; ++r) a[r] = fma(-f, vb[r], a[r]);
-    // right-hand side: rows dealt over the W lanes
-    T py = T(0);
-#pragma unroll
-    for (int r = lc; r < QMAX; r += W) py += (r >= E) ? vb[r] * yb[r] : T(0);
-#pragma unroll
-    for (int o = W / 2; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
-    const T fy = py * inv;
-#pragma unroll
-    for (int r = lc; r < QMAX; r += W)
-      if (r >= E) yb[r] = fma(-fy, vb[r], yb[r]);
-    __syncwarp();
+  for (int r = 0; r < QMAX; ++r) {
+    const T v = (r >= E) ? a[r] : T(0);
+    sg4[r & 3] = fma(v, v, sg4[r & 3]);
+    alp = (r == E) ? a[r] : alp;
   }
-}
-
-template <typename T, int W, int QMAX, int... Es>
-__device__ __forceinline__ void k2c_all_steps(T (&a)[QMAX], T cn, T* vb, T* yb, int lc, int kk, int kkw,
-                                              bool& bad, std::integer_sequence<int, Es...>) {
-  (k2c_step<T, W, QMAX, Es>(a, cn, vb, yb, lc, kk, kkw, bad), ...);
+  const T sig = (sg4[0] + sg4[1]) + (sg4[2] + sg4[3]);
+  const bool act = sig > cn * K2Tol<T>::v;
+  const T sg = act ? sig : T(1);
+  const T nrm = sg * k2_rsqrt(sg);
+  const T beta = (alp >= T(0)) ? -nrm : nrm;
+  const T inv_o = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
+  if (lc == E) {                                          // owner publishes v: 0 above the pivot
+#pragma unroll
+    for (int r = 0; r < QMAX; ++r) vb[r] = (r > E) ? a[r] : ((r == E) ? alp - beta : T(0));
+  }
+  const T inv = __shfl_sync(0xffffffffu, inv_o, E, W);
+  bad |= (E < kk) && (inv == T(0));
+  __syncwarp();
+  // trailing columns (lanes > E): dot, update
+  T dt4[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+  for (int r = 0; r < QMAX; ++r) dt4[r & 3] = fma(vb[r], a[r], dt4[r & 3]);
+  const T dot = (dt4[0] + dt4[1]) + (dt4[2] + dt4[3]);
+  const T f = (lc > E) ? dot * inv : T(0);
+#pragma unroll
+  for (int r = 0; r < QMAX; ++r) a[r] = fma(-f, vb[r], a[r]);
+  // right-hand side: rows dealt over the W lanes
+  T py = T(0);
+#pragma unroll
+  for (int r = lc; r < QMAX; r += W) py = fma(vb[r], yb[r], py);
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+  const T fy = py * inv;
+#pragma unroll
+  for (int r = lc; r < QMAX; r += W) yb[r] = fma(-fy, vb[r], yb[r]);
+  __syncwarp();
 }
 
 template <typename T, int W, int QMAX>
@@ -346,7 +343,8 @@ k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* _
       for (int r = lc; r < QMAX; r += W) yb[r] = (r == diag) ? T(1) : T(0);
       __syncwarp();
       bool bad = false;
-      k2c_all_steps<T, W, QMAX>(a, cn, vb, yb, lc, kk, kkw, bad, std::make_integer_sequence<int, W>{});
+#pragma unroll 1
+      for (int E = 0; E < kkw; ++E) k2c_step<T, W, QMAX>(a, cn, vb, yb, lc, kk, E, bad);
       T r2 = T(0);
 #pragma unroll
       for (int r = lc; r < QMAX; r += W) r2 += (r >= kk) ? yb[r] * yb[r] : T(0);

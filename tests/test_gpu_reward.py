@@ -305,3 +305,40 @@ def test_host_entry_trims_padding_exactly():
     kept = orc.kept_edge_mask(p.num_edges, acts[5])
     assert not kept[7] and int(dev["nnz_m"][3]) == p.num_edges
     ctx.close()
+
+
+def test_rank_deficient_tiles_are_handed_to_the_generic_kernel():
+    """The column-per-lane ls kernel assumes full column rank; a singular A
+    (two identical rows) makes some tiles rank-deficient: those (row, trajectory)
+    pairs must be redone by the generic kernel and still match LAPACK."""
+    rng = np.random.default_rng(11)
+    n = 64
+    a = sp.random(n, n, density=0.08, random_state=4, format="lil") + sp.identity(n, format="lil") * 2.0
+    a = sp.lil_matrix(a)
+    a[5, :] = a[3, :]                                   # rows 3 and 5 identical -> dependent columns
+    a = sp.csr_matrix(a)
+    a.sort_indices()
+    rows, cols = [], []
+    for i in range(n):
+        base = [3, 5] if i % 3 == 0 else []
+        extra = rng.choice([c for c in range(n) if c not in (3, 5)], size=10, replace=False)
+        cc = np.array(base + list(extra))
+        rows.append(np.full(cc.size, i))
+        cols.append(cc)
+    r = np.concatenate(rows).astype(np.int64)
+    c = np.concatenate(cols).astype(np.int64)
+    v = rng.uniform(-1, 1, r.size)
+    coo = a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(n, r, c, v, coo.row, coo.col, coo.data)
+    info = ctx.info()
+    assert info.ls_class_rows[2] + info.ls_class_rows[3] > 0        # column-per-lane classes in use
+    acts = synth.make_trajectories(r.size, 6, seed0=2, max_frac=0.2)
+    acts[0, :] = -1                                                  # everything kept: rows 0,3,6.. are deficient
+    want = orc.reward_batch_ls(n, r, c, a, acts, 0.5, dtype=np.float64, baseline_dtype=np.float64)
+    got = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "ls", torch.float64)
+    np.testing.assert_allclose(got["residual"].cpu().numpy(), want["residual"], rtol=1e-9, atol=1e-9)
+    want32 = orc.reward_batch_ls(n, r, c, a, acts, 0.5, dtype=np.float32, baseline_dtype=np.float32)
+    got32 = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "ls", torch.float32)
+    np.testing.assert_allclose(got32["reward"].cpu().numpy(), want32["reward"], rtol=1e-4, atol=5e-2)
+    ctx.close()
