@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=96, help="trajectories in the CPU-baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip the ls-mode side measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-frac", type=float, default=0.0,
+                    help="trajectory b deletes floor(u_b*E*max_frac) edges (0 = 0.5; cfg5: 0.01)")
     return ap.parse_args()
 
 
@@ -126,7 +128,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # synthetic trajectories on the device (seeded per global trajectory index)
 # ---------------------------------------------------------------------------
-def device_trajectories(num_edges, batch, first, device):
+def device_trajectories(num_edges, batch, first, device, max_frac=0.5):
     import torch
     lens = []
     gens = []
@@ -134,7 +136,7 @@ def device_trajectories(num_edges, batch, first, device):
         g = torch.Generator(device=device)
         g.manual_seed(1000 + first + b)
         u = float(torch.rand(1, generator=g, device=device))
-        lens.append(int(np.floor(u * num_edges * 0.5)))
+        lens.append(int(np.floor(u * num_edges * max_frac)))
         gens.append(g)
     tmax = max(lens) + 1
     acts = torch.full((batch, tmax), -1, dtype=torch.int64, device=device)
@@ -297,7 +299,8 @@ def run_b200_arm(args):
     t0 = time.perf_counter()
     ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, device=local)
     setup_s = time.perf_counter() - t0
-    acts = device_trajectories(p.num_edges, batch, rank * batch, dev)     # weak scaling: B per GPU
+    max_frac = args.max_frac or (0.01 if args.config == "cfg5" else 0.5)
+    acts = device_trajectories(p.num_edges, batch, rank * batch, dev, max_frac)     # weak scaling: B per GPU
     B, T = acts.shape
     gathered = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)         # > 126 MB L2
@@ -402,7 +405,7 @@ def run_b200_arm(args):
     # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
     extras = {}
     if rank == 0 and not args.no_extras and args.mode == "copy":
-        sub = acts[: min(B, 1024)]
+        sub = acts[: min(B, 1024 if args.config in ("cfg1", "cfg2") else 64)]
         for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("copy", torch.float64)):
             try:
                 for _ in range(2):
@@ -435,7 +438,7 @@ def run_b200_arm(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args, p, B), "mode": args.mode, "n": p.n, "num_edges": p.num_edges,
-                       "batch_per_gpu": B, "max_trajectory_len": T, "alpha": 0.5,
+                       "batch_per_gpu": B, "max_trajectory_len": T, "alpha": 0.5, "max_deleted_fraction": max_frac,
                        "parallelism": f"trajectory-sharded x{world}",
                        "l2": "256 MiB flush between timed iterations; actions (B*T*8 B) exceed L2",
                        "timing": "CUDA events per step on the launch stream, max over ranks"},
