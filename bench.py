@@ -425,7 +425,18 @@ def run_b200_arm(args):
                 extras[f"{md}/{dt}"] = {"error": str(exc)}
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1:
+        # the CPU leg doubles as an in-run check that the timed kernels do the work:
+        # two of the timed trajectories re-scored by the oracle
+        from oracle import spai_oracle as orc
+        sel = acts[:2].cpu().numpy()
+        if args.mode == "copy":
+            npdt = np.float32 if args.dtype == "f32" else np.float64
+            want = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val.astype(npdt), p.a.astype(npdt),
+                                         sel, 0.5, dtype=npdt)["reward"]
+            got = ctx.reward_batch(acts[:2], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
+            parity = {"trajectories": 2, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
         v, dt = cpu_port_throughput(args.config, args.scale, args.cpu_sample, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{args.cpu_sample} trajectories of the same workload, copy/fp32, numpy/scipy oracle "
@@ -450,6 +461,7 @@ def run_b200_arm(args):
             "kernels": kern,
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "parity_check": parity,
             "extras": extras,
             "context": {"setup_s": setup_s, "plan_contributions": int(info.contributions),
                         "device_bytes": int(info.device_bytes), "max_row_union": int(info.max_row_union),

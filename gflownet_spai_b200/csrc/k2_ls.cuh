@@ -224,49 +224,51 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
 // One Householder step; E is a RUNTIME value (the step loop is not unrolled: a
 // fully unrolled 32-step body is ~180 KB of straight-line SASS that every warp
 // streams once per problem — instruction fetch became the bottleneck). Register
-// indices stay static because every row loop runs over all QMAX rows; rows
-// above the pivot are neutralised by zeros in the published reflector.
+// indices stay static because the column is SHIFTED UP by one row per step (the
+// update writes row r into register r-1, the finished pivot row drops out and a
+// zero enters at the bottom): the pivot is always a[0], the live rows are always
+// a[0 .. QMAX-1-E], and no per-row predicates or selects are needed (a version
+// with `r >= E` selects issued 2.2x more instructions, ALU-pipe bound per ncu).
+// The right-hand side lives in shared memory and is indexed with the offset E.
 template <typename T, int W, int QMAX>
 __device__ __forceinline__ void k2c_step(T (&a)[QMAX], T cn, T* __restrict__ vb, T* __restrict__ yb,
                                          int lc, int kk, int E, bool& bad) {
   T sg4[4] = {T(0), T(0), T(0), T(0)};                    // 4 chains: FMA latency binds at low occupancy
-  T alp = T(0);
 #pragma unroll
-  for (int r = 0; r < QMAX; ++r) {
-    const T v = (r >= E) ? a[r] : T(0);
-    sg4[r & 3] = fma(v, v, sg4[r & 3]);
-    alp = (r == E) ? a[r] : alp;
-  }
+  for (int r = 0; r < QMAX; ++r) sg4[r & 3] = fma(a[r], a[r], sg4[r & 3]);
   const T sig = (sg4[0] + sg4[1]) + (sg4[2] + sg4[3]);
+  const T alp = a[0];
   const bool act = sig > cn * K2Tol<T>::v;
   const T sg = act ? sig : T(1);
   const T nrm = sg * k2_rsqrt(sg);
   const T beta = (alp >= T(0)) ? -nrm : nrm;
   const T inv_o = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
-  if (lc == E) {                                          // owner publishes v: 0 above the pivot
+  if (lc == E) {                                          // owner publishes v
+    vb[0] = alp - beta;
 #pragma unroll
-    for (int r = 0; r < QMAX; ++r) vb[r] = (r > E) ? a[r] : ((r == E) ? alp - beta : T(0));
+    for (int r = 1; r < QMAX; ++r) vb[r] = a[r];
   }
   const T inv = __shfl_sync(0xffffffffu, inv_o, E, W);
   bad |= (E < kk) && (inv == T(0));
   __syncwarp();
-  // trailing columns (lanes > E): dot, update
+  // trailing columns (lanes > E): dot, update + shift
   T dt4[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
   for (int r = 0; r < QMAX; ++r) dt4[r & 3] = fma(vb[r], a[r], dt4[r & 3]);
   const T dot = (dt4[0] + dt4[1]) + (dt4[2] + dt4[3]);
   const T f = (lc > E) ? dot * inv : T(0);
 #pragma unroll
-  for (int r = 0; r < QMAX; ++r) a[r] = fma(-f, vb[r], a[r]);
-  // right-hand side: rows dealt over the W lanes
+  for (int r = 1; r < QMAX; ++r) a[r - 1] = fma(-f, vb[r], a[r]);
+  a[QMAX - 1] = T(0);
+  // right-hand side: live rows E .. QMAX-1 dealt over the W lanes
   T py = T(0);
 #pragma unroll
-  for (int r = lc; r < QMAX; r += W) py = fma(vb[r], yb[r], py);
+  for (int r = lc; r < QMAX; r += W) py = fma(vb[r], yb[E + r], py);
 #pragma unroll
   for (int o = W / 2; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
   const T fy = py * inv;
 #pragma unroll
-  for (int r = lc; r < QMAX; r += W) yb[r] = fma(-fy, vb[r], yb[r]);
+  for (int r = lc; r < QMAX; r += W) yb[E + r] = fma(-fy, vb[r], yb[E + r]);
   __syncwarp();
 }
 
@@ -284,7 +286,7 @@ k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* _
   __shared__ __align__(16) T tile[QMAX * W];       // [row][slot]
   __shared__ T coln2[W];
   __shared__ __align__(16) T vbuf[GROUPS][QMAX];
-  __shared__ __align__(16) T ybuf[GROUPS][QMAX];
+  __shared__ __align__(16) T ybuf[GROUPS][QMAX + W];      // + W: step E reads rows E .. E+QMAX-1
   __shared__ double totsm[K2_MAX_NTG * GROUPS];
 
   const int tid = threadIdx.x;
@@ -340,7 +342,7 @@ k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* _
       for (int r = 0; r < QMAX; ++r) a[r] = (e >= 0) ? tile[r * W + e] : T(0);
       const T cn = (e >= 0) ? coln2[e] : T(0);
 #pragma unroll
-      for (int r = lc; r < QMAX; r += W) yb[r] = (r == diag) ? T(1) : T(0);
+      for (int r = lc; r < QMAX + W; r += W) yb[r] = (r == diag) ? T(1) : T(0);
       __syncwarp();
       bool bad = false;
 #pragma unroll 1
