@@ -307,7 +307,7 @@ def run_b200_arm(args):
 
     def step_dev():
         out = ctx.reward_batch(acts, 0.5, args.mode, tdtype)
-        if world > 1:
+        if world > 1 and not os.environ.get("SPAI_BENCH_NO_GATHER"):
             dist.all_gather_into_tensor(gathered, out["reward"])
         return out
 
@@ -320,8 +320,7 @@ def run_b200_arm(args):
         out = step_dev()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                                   # every rank samples its own GPU
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
@@ -332,8 +331,18 @@ def run_b200_arm(args):
         ev[s][1].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        sm = [c["sm_mhz"] for c in allc if c and c["sm_mhz"]]
+        clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clocks["sm_max_mhz"],
+                  "reasons": sorted({r for c in allc if c for r in c["reasons"]}),
+                  "samples": sum(c["samples"] for c in allc if c), "per_rank_sm_mhz": [c["sm_mhz"] if c else None for c in allc]}
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if os.environ.get("SPAI_BENCH_DEBUG"):
+        print(f"[rank {rank}] T={T} valid={int((acts >= 0).sum())} clocks={clocks}", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] per-step ms: {[round(a.elapsed_time(b), 3) for a, b in ev]}", file=sys.stderr, flush=True)
     launches = ctx.last_timing().launches * args.steps
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -437,6 +446,21 @@ def run_b200_arm(args):
                                          sel, 0.5, dtype=npdt)["reward"]
             got = ctx.reward_batch(acts[:2], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
             parity = {"trajectories": 2, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
+        # ls-mode CPU restatement (LAPACK lstsq per row), bounded sample: 2048 rows of one pattern
+        try:
+            import scipy.sparse as _sp
+            kept = orc.kept_edge_mask(p.num_edges, sel[0])
+            pat = orc.build_pattern_matrix(p.n, p.edge_row, p.edge_col, np.ones(p.num_edges), kept, np.float64)
+            rows_s = np.linspace(0, p.n - 1, num=min(p.n, 2048), dtype=np.int64)
+            t0 = time.perf_counter()
+            for i in rows_s:
+                orc.ls_row_residual2(p.a, int(i), np.unique(pat.indices[pat.indptr[i]:pat.indptr[i + 1]]))
+            dt_ls = time.perf_counter() - t0
+            extras["ls_cpu_port/f64"] = {"row_solves_per_s": rows_s.size / dt_ls,
+                                         "patterns_per_s": rows_s.size / dt_ls / p.n, "cores": 1,
+                                         "sample": f"{rows_s.size} rows of one pattern, numpy.linalg.lstsq"}
+        except Exception as exc:
+            extras["ls_cpu_port/f64"] = {"error": str(exc)}
         v, dt = cpu_port_throughput(args.config, args.scale, args.cpu_sample, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{args.cpu_sample} trajectories of the same workload, copy/fp32, numpy/scipy oracle "

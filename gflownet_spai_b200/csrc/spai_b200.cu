@@ -333,6 +333,27 @@ struct EvalShape {       // launch geometry of one reward evaluation over Bc tra
   bool has_column_class = false;      // column-per-lane kernels may hand tiles to the generic kernel
 };
 
+// resident CTAs per SM of the copy kernel instantiation (occupancy API, cached):
+// the grid is sized to ONE full wave so no half-empty second wave trails.
+static int k3_blocks_per_sm(int dtype, int nt) {
+  static int cache[2][9] = {};
+  int& c = cache[dtype == SPAI_F64][nt];
+  if (c) return c;
+  int v = 0;
+  const size_t smem = (size_t)K3_SMEM_BYTES;
+#define SPAI_OCC(T, NT) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k3_copy_kernel<T, NT>, K3_THREADS, smem)
+  if (dtype == SPAI_F32) {
+    if (nt == 8) SPAI_OCC(float, 8); else if (nt == 4) SPAI_OCC(float, 4);
+    else if (nt == 2) SPAI_OCC(float, 2); else SPAI_OCC(float, 1);
+  } else {
+    if (nt == 4) SPAI_OCC(double, 4); else if (nt == 2) SPAI_OCC(double, 2); else SPAI_OCC(double, 1);
+  }
+#undef SPAI_OCC
+  if (cudaGetLastError() != cudaSuccess || v <= 0) v = 4;
+  c = v;
+  return c;
+}
+
 static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, int sm_count) {
   EvalShape s;
   if (mode == SPAI_MODE_COPY) {
@@ -341,7 +362,7 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     s.Bp = round_up(Bc, (int64_t)K3_THREADS * s.nt);
     const int64_t Bp = s.Bp;
     s.gy = (int)ceil_div(Bp, (int64_t)K3_THREADS * s.nt);
-    const int target = sm_count * 8;
+    const int target = sm_count * k3_blocks_per_sm(dtype, s.nt);     // one full wave
     s.gx = (int)std::max<int64_t>(1, std::min<int64_t>(plan.ntiles, std::max(1, target / s.gy)));
     s.parts = s.gx;
   } else {
@@ -760,6 +781,10 @@ struct RowTrimmer {          // worker threads publish lengths group by group
       : len(B), ready((size_t)ceil_div(std::max<int64_t>(B, 1), GROUP)) {
     for (auto& r : ready) r.store(0, std::memory_order_relaxed);
     int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {        // one process per GPU shares the host cores
+      const int lw = atoi(e);
+      if (lw > 1) nt = std::max(2, nt / lw);
+    }
     if (const char* e = getenv("SPAI_HOST_THREADS")) nt = atoi(e);
     nt = std::max(1, std::min(nt, 32));
     const int64_t ngroups = (int64_t)ready.size();
