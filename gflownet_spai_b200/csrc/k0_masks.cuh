@@ -87,9 +87,14 @@ k0_mask_build_smem_kernel(const int64_t* __restrict__ actions, int64_t B, int64_
       atomicAnd(&k0_sm[s >> 5], ~(1u << (s & 31)));
     }
   };
-  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-    const longlong2* row2 = reinterpret_cast<const longlong2*>(row);
-    const int64_t T2 = T >> 1;
+  {
+    // rows are 8-byte aligned; peel one element when the row starts in the middle
+    // of a 16-byte granule (odd T makes every other row start there)
+    const int head = (reinterpret_cast<uintptr_t>(row) & 15) ? 1 : 0;
+    if (head && tid == 0 && T > 0) clear(row[0]);
+    const int64_t Tv = (T > head) ? T - head : 0;
+    const longlong2* row2 = reinterpret_cast<const longlong2*>(row + head);
+    const int64_t T2 = Tv >> 1;
     constexpr int LD = 8;                 // independent 16-byte loads in flight per thread
     int64_t t = tid;
     for (; t + (int64_t)(LD - 1) * K0S_THREADS < T2; t += (int64_t)LD * K0S_THREADS) {
@@ -104,10 +109,7 @@ k0_mask_build_smem_kernel(const int64_t* __restrict__ actions, int64_t B, int64_
       clear(v.x);
       clear(v.y);
     }
-    if ((T & 1) && tid == 0) clear(row[T - 1]);
-  } else {
-#pragma unroll 4
-    for (int64_t t = tid; t < T; t += K0S_THREADS) clear(__ldcs(row + t));
+    if ((Tv & 1) && tid == 0) clear(row[T - 1]);
   }
   __syncthreads();
   long long cnt = 0;
