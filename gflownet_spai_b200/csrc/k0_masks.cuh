@@ -155,7 +155,9 @@ __global__ void k0_mask_from_taken_kernel(const uint32_t* __restrict__ taken, in
   }
 }
 
-// mask u32[B][W] -> maskT u32[W][Bp]; columns b in [B, Bp) are written as 0.
+// mask u32[B][W] -> maskT u32[W][Bp]; the padding columns b in [B, Bp) are written as
+// all-ones ("nothing removed") so they never defeat the untouched-row vote of K3;
+// their results are discarded.
 __global__ void __launch_bounds__(256)
 k0_transpose_kernel(const uint32_t* __restrict__ mask, int64_t B, int64_t W,
                     uint32_t* __restrict__ maskT, int64_t Bp) {
@@ -165,7 +167,7 @@ k0_transpose_kernel(const uint32_t* __restrict__ mask, int64_t B, int64_t W,
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {
     const int64_t b = b0 + r, w = w0 + tx;
-    tile[r][tx] = (b < B && w < W) ? mask[b * W + w] : 0u;
+    tile[r][tx] = (w < W) ? ((b < B) ? mask[b * W + w] : 0xffffffffu) : 0u;
   }
   __syncthreads();
 #pragma unroll

@@ -83,6 +83,28 @@ __device__ __forceinline__ void k3_cond_add(double& acc, uint32_t m, uint32_t eb
       : "r"(m), "r"(ebit), "d"(w));
 }
 
+// Row residual^2 with EVERY candidate kept, one thread per row, same operation
+// order as the main kernel. Used for the incremental fast path: a row none of
+// whose slots was removed by any trajectory of the warp is not re-evaluated.
+template <typename T>
+__global__ void k3_row_base_kernel(const typename RecOf<T>::type* __restrict__ recs,
+                                   const int64_t* __restrict__ cptr, const RowHdr* __restrict__ rhdr,
+                                   int64_t n, T* __restrict__ base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T acc = (rhdr[i].flags & 1) ? T(-1) : T(0);
+  T rs = T(0);
+  for (int64_t c = cptr[i]; c < cptr[i + 1]; ++c) {
+    const auto r = recs[c];
+    acc += rec_w(r);
+    if (r.flags & F_END) {
+      rs = fma(acc, acc, rs);
+      acc = (r.flags & F_NEXT_DIAG) ? T(-1) : T(0);
+    }
+  }
+  base[i] = rs;
+}
+
 // The per-lane mask window: words wcur and wcur+1 of every trajectory handled by
 // the lane (trajectory j of the lane is column `j * K3_THREADS` after `mp`);
 // advanced monotonically as the rows walk through the slot range.
@@ -121,7 +143,7 @@ struct MaskWindow {
 // callers guarantee one readable record past the end.
 template <typename T, int NT, typename Rec>
 __device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt, int sp, int k,
-                                            bool first_diag, MaskWindow<NT>& mw,
+                                            bool first_diag, T base, MaskWindow<NT>& mw,
                                             const uint32_t* __restrict__ mp, int64_t Bp, int64_t W,
                                             T (&rs)[NT]) {
   mw.seek(mp, Bp, W, sp >> 5);
@@ -130,10 +152,18 @@ __device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt,
   uint32_t m[NT];
   T acc[NT];
   const T a0 = first_diag ? T(-1) : T(0);
+  uint32_t all = kmask;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     m[j] = __funnelshift_r(mw.lo[j], mw.hi[j], sh) & kmask;
+    all &= m[j];
     acc[j] = a0;
+  }
+  // incremental path: the row is untouched by every trajectory of this warp
+  if (__all_sync(0xffffffffu, all == kmask)) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) rs[j] += base;
+    return;
   }
   int c = 0;
   while (c < cnt) {
@@ -186,7 +216,8 @@ __device__ __forceinline__ void k3_row_wide(const Rec* __restrict__ rp, int cnt,
 template <typename T, int NT>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
-               const RowHdr* __restrict__ rhdr, const int32_t* __restrict__ tile_row, int ntiles,
+               const RowHdr* __restrict__ rhdr, const T* __restrict__ row_base,
+               const int32_t* __restrict__ tile_row, int ntiles,
                const uint32_t* __restrict__ maskT, int64_t Bp, int64_t W,
                double* __restrict__ partial) {
   using Rec = typename RecOf<T>::type;
@@ -247,8 +278,9 @@ k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* 
       if (h.cnt == 0) continue;
       const bool fd = h.flags & 1;
       if (h.k <= 32) {
-        if (staged) k3_row_fast<T, NT, Rec>(tile + off, h.cnt, h.sp, h.k, fd, mw, mp, Bp, W, rs);
-        else        k3_row_fast<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, h.k, fd, mw, mp, Bp, W, rs);
+        const T base = row_base[r0 + i];
+        if (staged) k3_row_fast<T, NT, Rec>(tile + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, rs);
+        else        k3_row_fast<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, rs);
       } else {
         if (staged) k3_row_wide<T, NT, Rec>(tile + off, h.cnt, h.sp, fd, mp, Bp, rs);
         else        k3_row_wide<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, fd, mp, Bp, rs);

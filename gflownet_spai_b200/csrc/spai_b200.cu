@@ -240,6 +240,20 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
                                                     plan.cptr, plan.c_col, plan.rec_copy, plan.rec_ls, plan.r_q, plan.r_diag, plan.rhdr);
     SPAI_CUDA(cudaGetLastError());
   }
+  if (dtype == SPAI_F32) {
+    float* rb = nullptr;
+    SPAI_TRY(ar.alloc(&rb, n));
+    k3_row_base_kernel<float><<<(unsigned)ceil_div(std::max<int64_t>(n, 1), 256), 256, 0, st>>>(
+        reinterpret_cast<const Rec32*>(plan.rec_copy), plan.cptr, plan.rhdr, n, rb);
+    plan.row_base = rb;
+  } else {
+    double* rb = nullptr;
+    SPAI_TRY(ar.alloc(&rb, n));
+    k3_row_base_kernel<double><<<(unsigned)ceil_div(std::max<int64_t>(n, 1), 256), 256, 0, st>>>(
+        reinterpret_cast<const Rec64*>(plan.rec_copy), plan.cptr, plan.rhdr, n, rb);
+    plan.row_base = rb;
+  }
+  SPAI_CUDA(cudaGetLastError());
   std::vector<int32_t> hq(n), hd(n);
   SPAI_CUDA(cudaMemcpyAsync(hq.data(), plan.r_q, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPAI_CUDA(cudaMemcpyAsync(hd.data(), plan.r_diag, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -490,7 +504,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
 #define SPAI_K3(T, NT)                                                                          \
   k3_copy_kernel<T, NT><<<grid, K3_THREADS, smem, st>>>(                                        \
       reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, plan.rhdr,    \
-      plan.tile_row, plan.ntiles, maskT, Bp, W, partial)
+      reinterpret_cast<const T*>(plan.row_base), plan.tile_row, plan.ntiles, maskT, Bp, W, partial)
     if (plan.ntiles == 0) {
       SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)s.parts * Bp * 8, st));
     } else if (dtype == SPAI_F32) {

@@ -119,6 +119,7 @@ struct Plan {
   int32_t* r_q = nullptr;         // [n] |I_i|
   int32_t* r_diag = nullptr;      // [n] segment index of column i, or -1
   RowHdr* rhdr = nullptr;         // [n]
+  void* row_base = nullptr;       // [n] T: row residual^2 with every candidate kept (copy mode)
   int64_t rows_missing_diag = 0;  // rows with r_diag < 0 (each adds 1 to ||.||^2)
   int max_q = 0;
   int max_k = 0;

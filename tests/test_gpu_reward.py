@@ -342,3 +342,29 @@ def test_rank_deficient_tiles_are_handed_to_the_generic_kernel():
     got32 = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "ls", torch.float32)
     np.testing.assert_allclose(got32["reward"].cpu().numpy(), want32["reward"], rtol=1e-4, atol=5e-2)
     ctx.close()
+
+
+def test_short_trajectories_take_the_untouched_row_path():
+    """Incremental evaluation: rows none of whose slots was removed by any
+    trajectory of a warp are not re-evaluated (their all-kept residual is cached
+    per context). Few deletions per trajectory => almost every row is skipped."""
+    p = synth.make_problem("cfg2", scale=0.25)           # 64 x 64 grid
+    coo = p.a.tocoo()
+    from gflownet_spai_b200.env import SpaiContext
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data)
+    rng = np.random.default_rng(8)
+    bsz = 40
+    acts = np.full((bsz, 9), -1, dtype=np.int64)
+    for b in range(bsz):
+        n_del = int(rng.integers(0, 6))
+        acts[b, :n_del] = rng.integers(0, p.num_edges, n_del)
+        acts[b, n_del] = p.num_edges
+    t = torch.from_numpy(acts).cuda()
+    want64 = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val, p.a, acts, 0.5, dtype=np.float64)
+    got64 = ctx.reward_batch(t, 0.5, "copy", torch.float64)
+    np.testing.assert_allclose(got64["residual"].cpu().numpy(), want64["residual"], rtol=RTOL64, atol=ATOL64)
+    want32 = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val.astype(np.float32),
+                                   p.a.astype(np.float32), acts, 0.5, dtype=np.float32)
+    got32 = ctx.reward_batch(t, 0.5, "copy", torch.float32)
+    np.testing.assert_allclose(got32["reward"].cpu().numpy(), want32["reward"], rtol=RTOL32, atol=ATOL32)
+    ctx.close()
