@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(K2_NW * 32)
 k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
              const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
              const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
-             int64_t Bp, int ntg, double* __restrict__ partial) {
+             int64_t Bp, int ntg, double* __restrict__ partial, const double* __restrict__ row_base) {
   using Rec = typename RecOf<T>::type;
   constexpr int QP = QL * G;
   constexpr int NG = 32 / G;
@@ -172,6 +172,11 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
       const uint32_t lo = maskT[w0 * Bp + b];
       const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
       const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
+      // incremental path: no problem of this warp lost a candidate of this row
+      if (__all_sync(0xffffffffu, m == kmask)) {
+        if (lg == 0) totsm[j * GROUPS + gid] += row_base[i];
+        continue;
+      }
 
       // compact the kept columns to the front: column c' <- c'-th kept slot
       T a[QL][KMAX];
@@ -278,7 +283,8 @@ k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* _
               const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
               const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
               int64_t Bp, int64_t B, int ntg, double* __restrict__ partial, int2* __restrict__ fail_pairs,
-              unsigned int* __restrict__ fail_count, unsigned int fail_cap) {
+              unsigned int* __restrict__ fail_count, unsigned int fail_cap,
+              const double* __restrict__ row_base) {
   using Rec = typename RecOf<T>::type;
   constexpr int NP = 32 / W;                       // problems per warp
   constexpr int NTHREADS = K2_NW * 32;
@@ -334,6 +340,10 @@ k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* _
       const uint32_t lo = maskT[w0 * Bp + b];
       const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
       const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
+      if (__all_sync(0xffffffffu, m == kmask)) {            // incremental path (see k2_ls_kernel)
+        if (lc == 0) totsm[j * GROUPS + gid] += row_base[i];
+        continue;
+      }
       const int kk = __popc(m);
       const int kkw = __reduce_max_sync(0xffffffffu, kk);
       const int e = (lc < kk) ? (int)__fns(m, 0, lc + 1) : -1;       // my column = lc-th kept slot
@@ -390,7 +400,8 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
                      const uint32_t* __restrict__ maskT, int64_t Bp, int64_t B, T* work,
                      int64_t work_stride, int32_t* colmap, int64_t colmap_stride,
                      double* __restrict__ res2, const int2* __restrict__ pairs,
-                     const unsigned int* __restrict__ npairs, unsigned int pair_cap) {
+                     const unsigned int* __restrict__ npairs, unsigned int pair_cap,
+                     double* __restrict__ row_out) {
   using Rec = typename RecOf<T>::type;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -467,7 +478,10 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
     T r2 = T(0);
     for (int r = p + lane; r < q; r += 32) r2 = fma(y[r], y[r], r2);
     r2 = k2_wsum(r2);
-    if (lane == 0) atomicAdd(res2 + b, (double)r2);
+    if (lane == 0) {
+      if (row_out) row_out[i] = (double)r2;      // per-row mode (B == 1): all-kept baseline of the row
+      else atomicAdd(res2 + b, (double)r2);
+    }
     __syncwarp();
   }
 }

@@ -305,6 +305,44 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
     if (want_ls && !cls[c].empty()) SPAI_TRY(ar.upload(&plan.class_rows[c], cls[c]));
   }
   (void)ha;
+  if ((want_ls || dtype == SPAI_F32) && plan.rec_ls) {
+    // all-kept ls residual of every row (incremental path of the ls kernels): the generic
+    // solver in per-row mode over all rows with a non-empty union, one all-ones trajectory
+    SPAI_TRY(ar.alloc(&plan.row_base_ls, n));
+    SPAI_CUDA(cudaMemsetAsync(plan.row_base_ls, 0, (size_t)std::max<int64_t>(n, 1) * 8, st));
+    std::vector<int32_t> live;
+    for (int64_t i = 0; i < n; ++i) if (hq[i] > 0) live.push_back((int32_t)i);
+    if (!live.empty()) {
+      Arena t2;
+      int32_t* live_dev = nullptr;
+      SPAI_TRY(t2.upload(&live_dev, live));
+      const int64_t W = std::max<int64_t>(P.words(), 1), Bp = 32;
+      uint32_t* ones = nullptr;
+      SPAI_TRY(t2.alloc(&ones, W * Bp));
+      SPAI_CUDA(cudaMemsetAsync(ones, 0xff, (size_t)W * Bp * 4, st));
+      const int64_t warps = 148 * 16;
+      const int64_t wstride = std::max<int64_t>(plan.max_q, 1) * ((int64_t)P.max_k + 1);
+      int32_t* cmap = nullptr;
+      SPAI_TRY(t2.alloc(&cmap, warps * std::max<int64_t>(P.max_k, 1)));
+      if (dtype == SPAI_F32) {
+        float* work = nullptr;
+        SPAI_TRY(t2.alloc(&work, warps * wstride));
+        k2_ls_generic_kernel<float><<<(unsigned)(warps / 4), 128, 0, st>>>(
+            reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag, live_dev,
+            (int64_t)live.size(), ones, Bp, 1, work, wstride, cmap, std::max<int64_t>(P.max_k, 1), nullptr, nullptr,
+            nullptr, 0u, plan.row_base_ls);
+      } else {
+        double* work = nullptr;
+        SPAI_TRY(t2.alloc(&work, warps * wstride));
+        k2_ls_generic_kernel<double><<<(unsigned)(warps / 4), 128, 0, st>>>(
+            reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag, live_dev,
+            (int64_t)live.size(), ones, Bp, 1, work, wstride, cmap, std::max<int64_t>(P.max_k, 1), nullptr, nullptr,
+            nullptr, 0u, plan.row_base_ls);
+      }
+      SPAI_CUDA(cudaGetLastError());
+      SPAI_CUDA(cudaStreamSynchronize(st));      // scratch of t2 is released on return
+    }
+  }
   plan.bytes = ar.bytes;
   return SPAI_OK;
 }
@@ -432,13 +470,14 @@ static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const Eval
 #define SPAI_LS_ROW(IDX, KMAX, G, QL)                                                          \
   case IDX:                                                                                    \
     k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
-        plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial);             \
+        plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial,              \
+        plan.row_base_ls);                                                                     \
     break;
 #define SPAI_LS_COL(IDX, W, QMAX)                                                              \
   case IDX:                                                                                    \
     k2c_ls_kernel<T, W, QMAX><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,     \
         plan.class_rows[c], plan.class_count[c], maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs, \
-        fail_count, LS_FAIL_CAP);                                                              \
+        fail_count, LS_FAIL_CAP, plan.row_base_ls);                                            \
     break;
   switch (c) {
     SPAI_LS_ROW(0, 8, 4, 5)
@@ -470,7 +509,8 @@ struct PhaseTimer {
 static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, const uint32_t* mask,
                       int64_t Bc, char* scratch, int64_t scratch_bytes, int sm_count, double n_d,
                       double res0, double flops0, double alpha, double* reward, double* residual,
-                      int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches) {
+                      int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches,
+                      const long long* nnz_ready = nullptr) {
   const int64_t W = P.words();
   const EvalShape s = plan_shape(plan, mode, dtype, Bc, sm_count);
   const int64_t Bp = s.Bp;
@@ -486,8 +526,12 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
     SPAI_CUDA(cudaGetLastError()); ++nl;
   }
-  k0_popcount_kernel<<<(unsigned)Bc, 256, 0, st>>>(mask, W, Bc, nnz);
-  SPAI_CUDA(cudaGetLastError()); ++nl;
+  if (nnz_ready) {
+    SPAI_CUDA(cudaMemcpyAsync(nnz, nnz_ready, (size_t)Bc * 8, cudaMemcpyDeviceToDevice, st));   // popcount fused into K0
+  } else {
+    k0_popcount_kernel<<<(unsigned)Bc, 256, 0, st>>>(mask, W, Bc, nnz);
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+  }
   if (P.ndup) {
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(P.ndup * Bc, 256), 65535);
     k0_dup_correction_kernel<<<blocks, 256, 0, st>>>(mask, W, Bc, P.dup_start, P.dup_len, P.ndup, nnz);
@@ -556,13 +600,13 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
               reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
               plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
               reinterpret_cast<float*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
-              LS_FAIL_CAP);
+              LS_FAIL_CAP, nullptr);
         else
           k2_ls_generic_kernel<double><<<blocks, 128, 0, st>>>(
               reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
               plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
               reinterpret_cast<double*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
-              LS_FAIL_CAP);
+              LS_FAIL_CAP, nullptr);
         SPAI_CUDA(cudaGetLastError()); ++nl;
       }
     }
@@ -847,7 +891,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   int64_t Bc = B;
   auto need_for = [&](int64_t bc) {
     const int64_t bp = round_up(bc, 32);
-    int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4);                 // mask
+    int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4) + padded(bp * 8);   // mask + fused popcount
     if (src == FROM_ACTIONS_HOST) need += padded(bc * std::max<int64_t>(T, 1) * 8) + padded(bc * 4);
     if (out_host) need += 3 * padded(bp * 8);
     if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, dtype, bc, c->sm_count), W, dtype);
@@ -873,6 +917,8 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     const int64_t* act_dev = nullptr;
     int64_t act_ld = ld;
     const int32_t* row_len_dev = nullptr;
+    long long* nnz0 = cv.take<long long>(bp);
+    const long long* nnz_ready = nullptr;
     if (src == FROM_ACTIONS_HOST) {
       int64_t* buf = cv.take<int64_t>(bc * std::max<int64_t>(T, 1));
       int32_t* len_dev = cv.take<int32_t>(bc);
@@ -931,7 +977,8 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
           SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          K0S_MAX_SMEM));
           k0_mask_build_smem_kernel<<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(
-              act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nullptr, row_len_dev);
+              act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nnz0, row_len_dev);
+          nnz_ready = nnz0;
           SPAI_CUDA(cudaGetLastError()); ++launches;
         } else {
           const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
@@ -963,7 +1010,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     char* scratch = cv.take<char>(0);
     const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
     SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
-                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches));
+                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready));
     if (pt->on) cudaEventRecord(pt->ev[4], st);
     if (out_host) {
       if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));

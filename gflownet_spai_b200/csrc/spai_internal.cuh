@@ -120,6 +120,7 @@ struct Plan {
   int32_t* r_diag = nullptr;      // [n] segment index of column i, or -1
   RowHdr* rhdr = nullptr;         // [n]
   void* row_base = nullptr;       // [n] T: row residual^2 with every candidate kept (copy mode)
+  double* row_base_ls = nullptr;  // [n] the same for ls mode (re-solved row)
   int64_t rows_missing_diag = 0;  // rows with r_diag < 0 (each adds 1 to ||.||^2)
   int max_q = 0;
   int max_k = 0;

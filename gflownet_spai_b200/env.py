@@ -286,6 +286,12 @@ class PreconditionerEnv(Env):
         actions = actions.to(torch.int64)
         return self.ctx.reward_batch(actions, self._alpha(alpha), self.mode, self.dtype, want)
 
+    def update_from_taken(self, taken: torch.Tensor, alpha):
+        """Batch reward straight from the sampler's device-resident taken-bitmask
+        (int32 [B, words], edge order, bit set = edge removed): no action lists,
+        no host round trip."""
+        return self.ctx.reward_from_taken(taken, self._alpha(alpha), self.mode, self.dtype)
+
     def update(self, sparse_matrices, actions, alpha) -> list:
         """preconditioner.py:32-52: rewards of a batch of trajectories.
 

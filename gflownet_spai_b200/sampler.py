@@ -180,7 +180,8 @@ class GFlowNet(nn.Module):
         actions_tb = actions_tb[:t_len].contiguous()
         complete_actions = actions_tb.t().contiguous()            # [B, T] on the device
         al = float(alpha.detach()) if isinstance(alpha, torch.Tensor) else float(alpha)
-        rewards = self.env.update_tensor(complete_actions, al, want=("reward",))["reward"]
+        # the taken-bitmask IS the final state: score it directly (skips the actions -> mask kernel)
+        rewards = self.env.update_from_taken(taken, al)["reward"]
         if log is not None:
             log._actions = actions_tb.cpu()
             log._fwd_probs = self.chosen_probs(p, complete_actions.to(p.device))

@@ -367,4 +367,11 @@ def test_short_trajectories_take_the_untouched_row_path():
                                    p.a.astype(np.float32), acts, 0.5, dtype=np.float32)
     got32 = ctx.reward_batch(t, 0.5, "copy", torch.float32)
     np.testing.assert_allclose(got32["reward"].cpu().numpy(), want32["reward"], rtol=RTOL32, atol=ATOL32)
+    # the ls kernels skip untouched (row, warp) tiles the same way
+    wls = orc.reward_batch_ls(p.n, p.edge_row, p.edge_col, p.a, acts[:5], 0.5, dtype=np.float64,
+                              baseline_dtype=np.float64)
+    gls = ctx.reward_batch(t, 0.5, "ls", torch.float64)
+    np.testing.assert_allclose(gls["residual"].cpu().numpy()[:5], wls["residual"], rtol=1e-10, atol=1e-9)
+    gls32 = ctx.reward_batch(t, 0.5, "ls", torch.float32)
+    np.testing.assert_allclose(gls32["residual"].cpu().numpy()[:5], wls["residual"], rtol=1e-4)
     ctx.close()
