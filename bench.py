@@ -433,6 +433,29 @@ def run_b200_arm(args):
             except Exception as exc:        # report, never hide
                 extras[f"{md}/{dt}"] = {"error": str(exc)}
 
+    if rank == 0 and not args.no_extras and args.mode == "copy":
+        # early-training regime: short trajectories (64 deletions) -> most rows untouched -> incremental path
+        try:
+            g = torch.Generator(device=dev)
+            g.manual_seed(7)
+            short = torch.randint(0, p.num_edges, (B, 65), generator=g, device=dev, dtype=torch.int64)
+            short[:, -1] = p.num_edges
+            for md in ("copy", "ls"):
+                for _ in range(2):
+                    ctx.reward_batch(short, 0.5, md, tdtype)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(5):
+                    ctx.reward_batch(short, 0.5, md, tdtype)
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / 5
+                extras[f"{md}/{args.dtype} short trajectories (64 deletions, untouched rows skipped)"] = {
+                    "patterns_per_s": B / (ms / 1e3), "batch": int(B), "ms": ms}
+        except Exception as exc:
+            extras["short trajectories"] = {"error": str(exc)}
+
     cpu = None
     parity = None
     if rank == 0 and world == 1:
