@@ -149,4 +149,37 @@ k4_sample_kernel(const float* __restrict__ logits, int64_t logits_ld, int64_t A,
   }
 }
 
+// K4b — whole-trajectory sampling support (Gumbel-top-k / Plackett-Luce): drawing
+// ids one at a time from softmax(logits) without replacement until the terminal
+// id appears is, in distribution, the same as sorting the ids by
+// key_i = logit_i + Gumbel_i and cutting at the terminal's key. The set of
+// removed edges of sample b is therefore {i : key[b,i] > key[b,A-1]}: this kernel
+// packs that set (plus the terminal bit) into the sample's taken-bitmask with
+// warp ballots and counts it. One block row per sample, coalesced key reads.
+__global__ void __launch_bounds__(256)
+k4_pack_taken_kernel(const float* __restrict__ keys, int64_t ld, int64_t A,
+                     uint32_t* __restrict__ taken, int64_t words_ld, int32_t* __restrict__ length) {
+  const int64_t b = blockIdx.x;
+  const float* kb = keys + b * ld;
+  const float thr = kb[A - 1];
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  const int64_t words = (A + 31) >> 5;
+  for (int64_t w = threadIdx.x >> 5; w < words; w += blockDim.x >> 5) {
+    const int64_t i = w * 32 + lane;
+    const bool hit = i < A && (kb[i] > thr || i == A - 1);
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) taken[b * words_ld + w] = bal;
+    cnt += __popc(bal);
+  }
+  __shared__ int part[8];
+  if (lane == 0) part[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    length[b] = t;                       // ids drawn, terminal included
+  }
+}
+
 }  // namespace spai

@@ -1185,4 +1185,18 @@ int spai_sample_step_dev(spai_ctx* c, const float* logits, int64_t logits_ld, in
   return SPAI_OK;
 }
 
+int spai_pack_taken_dev(spai_ctx* c, const float* keys, int64_t keys_ld, int64_t A, int64_t B, uint32_t* taken,
+                        int64_t words_ld, int32_t* length, void* stream) {
+  if (!c || !keys || !taken || !length || A <= 0 || B < 0 || keys_ld < A || words_ld < (A + 31) / 32) {
+    set_error("spai_pack_taken_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  if (B == 0) return SPAI_OK;
+  DeviceGuard guard(c->device);
+  k4_pack_taken_kernel<<<(unsigned)B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(keys, keys_ld, A, taken,
+                                                                                       words_ld, length);
+  SPAI_CUDA(cudaGetLastError());
+  return SPAI_OK;
+}
+
 }  // extern "C"

@@ -203,6 +203,16 @@ class SpaiContext:
                                                   self._stream()), "spai_ls_solve_values_host")
         return out
 
+    def pack_taken(self, keys: torch.Tensor):
+        """keys f32[B, A] (CUDA) -> (taken int32[B, words], length int32[B]); see spai_pack_taken_dev."""
+        b, a = keys.shape
+        words = (a + 31) // 32
+        taken = torch.empty((b, words), dtype=torch.int32, device=keys.device)
+        length = torch.empty(b, dtype=torch.int32, device=keys.device)
+        check(self._lib.spai_pack_taken_dev(self._h, _ptr(keys), keys.stride(0), a, b, _ptr(taken), words,
+                                            _ptr(length), self._stream()), "spai_pack_taken_dev")
+        return taken, length
+
     def sample_step(self, logits, taken, uniforms, done, action, prob):
         """In-place masked categorical step on CUDA tensors (include/spai_b200.h)."""
         a = logits.shape[-1]

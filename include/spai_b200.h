@@ -156,6 +156,14 @@ int spai_sample_step_dev(spai_ctx* ctx, const float* logits_dev, int64_t logits_
                          uint8_t* done_dev, int64_t B, int64_t* action_dev, float* prob_dev,
                          void* stream);
 
+/* Whole-trajectory sampling support (Gumbel-top-k; equal in distribution to the
+ * step-by-step masked categorical draws of gflownet.py:135-179): given perturbed
+ * keys f32[B, keys_ld] (logit + Gumbel noise, column A-1 = terminal), writes the
+ * taken-bitmask u32[B, words_ld] of {i : key[b,i] > key[b,A-1]} plus the terminal
+ * bit, and length i32[B] = number of ids drawn (terminal included). */
+int spai_pack_taken_dev(spai_ctx* ctx, const float* keys_dev, int64_t keys_ld, int64_t A, int64_t B,
+                        uint32_t* taken_dev, int64_t words_ld, int32_t* length_dev, void* stream);
+
 /* Per-kernel device time of the LAST reward call on this context, in ms,
  * measured with CUDA events on the caller's stream (masks, transpose, reward
  * kernel, finalize) and the number of kernels launched by it. */

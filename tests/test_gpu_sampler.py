@@ -132,3 +132,67 @@ def test_sample_states_device_loop(small_env):
     loss.backward()
     assert torch.isfinite(fp.logit.grad).all() and float(fp.logit.grad.abs().sum()) > 0
     assert model.sample_states(s0, return_log=False) is None
+
+
+def test_pack_taken_kernel_matches_threshold_rule(small_env):
+    env, _ = small_env
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for a in (5, 461, 4100):
+        keys = torch.randn((7, a), device="cuda", generator=g)
+        taken, length = env.ctx.pack_taken(keys)
+        want = keys > keys[:, a - 1:a]
+        want[:, a - 1] = True
+        got = torch.zeros_like(want)
+        tw = taken.cpu().numpy().view(np.uint32)
+        for b in range(7):
+            bits = np.unpackbits(tw[b].view(np.uint8), bitorder="little")[:a]
+            got[b] = torch.from_numpy(bits.astype(bool)).cuda()
+        assert torch.equal(got, want)
+        assert torch.equal(length.to(torch.int64), want.sum(1))
+
+
+def test_gumbel_whole_trajectory_sampler(small_env):
+    """method='gumbel': same Log contract and, in distribution, the same
+    trajectories as the step sampler (Plackett-Luce equivalence)."""
+    from gflownet_spai_b200.sampler import GFlowNet, trajectory_balance_loss
+    env, init = small_env
+    a = env.num_actions
+    fp = _StubForward(a)
+    with torch.no_grad():
+        fp.logit[:] = -25.0                       # mass on ids 0..5 and the terminal id
+        fp.logit[:6] = torch.tensor([0.0, 0.5, 1.0, -0.5, 0.2, 0.8])
+        fp.logit[-1] = 1.2
+    model = GFlowNet(fp, _StubBackward(), env)
+    bsz = 24000
+    s0 = [init] * bsz
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    log = model.sample_states(s0, return_log=True, generator=gen, method="gumbel")
+    acts = log.actions.t()                        # [B, T]
+    assert acts.shape[0] == bsz and log.fwd_probs.shape == acts.shape
+    lens = (acts >= 0).sum(1)
+    last = acts.gather(1, (lens - 1)[:, None]).squeeze(1)
+    assert torch.all(last == a - 1)                                           # every trajectory ends at terminal
+    for b in range(0, bsz, 997):
+        row = acts[b, : int(lens[b])].tolist()
+        assert len(set(row)) == len(row) and all(x == -1 for x in acts[b, int(lens[b]):].tolist())
+    # first action ~ softmax(logits) (7 categories that carry the mass)
+    p = torch.softmax(fp.logit.detach(), 0).double().numpy()
+    cats = [0, 1, 2, 3, 4, 5, a - 1]
+    first = acts[:, 0].numpy()
+    counts = np.array([(first == c).sum() for c in cats], dtype=np.float64)
+    expect = bsz * p[cats]
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    assert counts.sum() >= bsz - 5 and chi2 < 27.9                            # chi2(6 dof) 99.99th percentile
+    # second action given the first: p_j / (1 - p_i) for a fixed first id
+    sel = first == 2
+    second = acts[sel, 1].numpy()
+    cats2 = [0, 1, 3, 4, 5, a - 1]
+    c2 = np.array([(second == c).sum() for c in cats2], dtype=np.float64)
+    e2 = sel.sum() * p[cats2] / (1 - p[2])
+    assert float(((c2 - e2) ** 2 / e2).sum()) < 25.7                          # chi2(5 dof) 99.99th percentile
+    # rewards equal a fresh evaluation of the logged actions; loss is differentiable
+    again = env.update_tensor(acts[:64].contiguous(), 0.5, want=("reward",))["reward"].float()
+    assert torch.allclose(log.rewards[:64], again, rtol=1e-5, atol=1e-3)
+    loss = trajectory_balance_loss(log.total_flow, log.rewards.clamp_min(1e-3), log.fwd_probs, log.back_probs)
+    loss.backward()
+    assert torch.isfinite(fp.logit.grad).all()
