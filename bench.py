@@ -268,8 +268,9 @@ def algorithmic_bytes(ctx, p, acts_dev, mode, wbytes):
     cost = 4.0 + (wbytes if mode == "copy" else 0.0) + 8.0 + rlen * (4.0 + wbytes)
     cost_t = torch.from_numpy(cost).to(acts_dev.device)
     total = 0.0
-    for b0 in range(0, acts_dev.shape[0], 256):
-        kept = ctx.kept_mask(acts_dev[b0:b0 + 256])
+    step = max(1, min(256, int(2e9 // (8 * max(1, p.num_edges)))))
+    for b0 in range(0, acts_dev.shape[0], step):
+        kept = ctx.kept_mask(acts_dev[b0:b0 + step])
         total += float((kept.to(torch.float64) @ cost_t).sum())
         del kept
     return total + 8.0 * acts_dev.shape[0]
