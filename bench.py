@@ -387,29 +387,41 @@ def run_b200_arm(args):
     # ---- end to end through the host entry point (pinned host actions in, rewards out)
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((B, T), dtype=torch.int64, pin_memory=True)
-        host.copy_(acts)
-        torch.cuda.synchronize()
-        for _ in range(2):
-            r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))   # syncs: result is on the host
+        ok, host = 1, None
+        try:
+            host = torch.empty((B, T), dtype=torch.int64, pin_memory=True)
+            host.copy_(acts)
+            torch.cuda.synchronize()
+        except Exception as exc:        # pinned-memory pressure with many ranks: report, never hide
+            ok, e2e = 0, {"error": f"{type(exc).__name__}: {exc}"}
+        if world > 1:                   # all ranks take the same branch (no collective mismatch)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag)
+        if ok:
+            for _ in range(2):
+                r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            e0.record()
+            for _ in range(args.steps):
+                r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))   # syncs: result is on the host
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, r["reward"].to(dev))
+            e1.record()
+            barrier()
+            e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
+            t_e = torch.tensor([e_ms], dtype=torch.float64, device=dev)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, r["reward"].to(dev))
-        e1.record()
-        barrier()
-        e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
-        t_e = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * args.steps / (float(t_e) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(B * T * 8), "d2h_bytes_per_step": int(B * 8),
-               "ms_per_step": float(t_e) / args.steps, "api": "SpaiContext.reward_batch(host int64 actions) "
-               "-> spai_reward_batch_host"}
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * B * args.steps / (float(t_e) / 1e3), "unit": UNIT,
+                   "h2d_bytes_per_step": int(ctx.last_timing().h2d_bytes), "d2h_bytes_per_step": int(B * 8),
+                   "input_bytes_per_step": int(B * T * 8), "ms_per_step": float(t_e) / args.steps,
+                   "api": "SpaiContext.reward_batch(pinned host int64 actions[B,T]) -> spai_reward_batch_host; "
+                          "the -1 padding of every row is trimmed on the host, so h2d_bytes < input bytes"}
+        elif e2e is None:
+            e2e = {"error": "pinned host allocation failed on another rank"}
         del host
 
     # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
