@@ -865,6 +865,42 @@ struct RowTrimmer {          // worker threads publish lengths group by group
   ~RowTrimmer() { for (auto& t : workers) t.join(); }
 };
 
+// K0 for rows [0, bc) of `act` (device-accessible pointer, leading dimension act_ld):
+// shared-memory bitmask per trajectory when it fits, else init + global RED.
+static int launch_k0(const Pattern& P, const int64_t* act, int64_t bc, int64_t T, int64_t act_ld,
+                     uint32_t* mask, long long* nnz0, const int32_t* row_len, cudaStream_t st, int* launches,
+                     bool* nnz_fused) {
+  const int64_t W = P.words();
+  static const int k0_variant = [] {
+    const char* v = getenv("SPAI_K0_VARIANT");
+    return !v ? 0 : (!strcmp(v, "red") ? 1 : (!strcmp(v, "smem") ? 2 : 0));
+  }();
+  const bool fits = W * 4 <= K0S_MAX_SMEM;
+  if (fits && k0_variant != 1 && T > 0) {
+    SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   K0S_MAX_SMEM));
+    k0_mask_build_smem_kernel<<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(
+        act, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nnz0, row_len);
+    SPAI_CUDA(cudaGetLastError()); ++*launches;
+    *nnz_fused = true;
+  } else {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
+    k0_mask_init_kernel<<<blocks, 256, 0, st>>>(mask, W, P.E, bc);
+    SPAI_CUDA(cudaGetLastError()); ++*launches;
+    if (T > 0) {
+      constexpr int U = 4;
+      const int64_t chunks_t = ceil_div(T, 256 * U);
+      const int64_t nblk = chunks_t * bc;
+      if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
+      k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
+          act, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t, row_len);
+      SPAI_CUDA(cudaGetLastError()); ++*launches;
+    }
+    *nnz_fused = false;
+  }
+  return SPAI_OK;
+}
+
 enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
 
 // Shared driver of the three reward entry points: chunk the batch so the scratch
@@ -919,23 +955,51 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     const int32_t* row_len_dev = nullptr;
     long long* nnz0 = cv.take<long long>(bp);
     const long long* nnz_ready = nullptr;
+    bool k0_done = false;
     if (src == FROM_ACTIONS_HOST) {
       int64_t* buf = cv.take<int64_t>(bc * std::max<int64_t>(T, 1));
       int32_t* len_dev = cv.take<int32_t>(bc);
       const int64_t* hbase = reinterpret_cast<const int64_t*>(input) + b0 * ld;
       act_ld = T;
       if (T >= 4096) {
-        // overlap: workers trim rows while this thread enqueues the prefix copies
+        // workers trim rows (scan back over the -1 padding) while this thread feeds the GPU
         if (!trimmer || trimmer_b0 != b0) { trimmer.reset(new RowTrimmer(hbase, bc, T, ld)); trimmer_b0 = b0; }
-        for (int64_t g = 0; g * RowTrimmer::GROUP < bc; ++g) {
-          trimmer->wait(g);
-          const int64_t hi = std::min(bc, (g + 1) * RowTrimmer::GROUP);
-          for (int64_t b = g * RowTrimmer::GROUP; b < hi; ++b) {
-            const int64_t n = trimmer->len[b];
-            if (n) SPAI_CUDA(cudaMemcpyAsync(buf + b * T, hbase + b * ld, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-          }
+        // zero-copy: pinned host memory is device-accessible (UVA), so K0 can stream the valid
+        // prefix of every row straight over PCIe into its shared-memory bitmask — no staging
+        // buffer and no per-row copy call. Pageable input falls back to per-row cudaMemcpyAsync.
+        const int64_t* hdev = nullptr;
+        static const bool force_memcpy = [] { const char* v = getenv("SPAI_H2D"); return v && !strcmp(v, "memcpy"); }();
+        if (!force_memcpy && W > 0) {
+          cudaPointerAttributes at;
+          if (cudaPointerGetAttributes(&at, hbase) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            hdev = reinterpret_cast<const int64_t*>(at.devicePointer);
+          else
+            cudaGetLastError();
         }
-        SPAI_CUDA(cudaMemcpyAsync(len_dev, trimmer->len.data(), (size_t)bc * 4, cudaMemcpyHostToDevice, st));
+        if (hdev) {
+          constexpr int64_t SG = 256;                                  // rows per K0 launch
+          if (pt->on) cudaEventRecord(pt->ev[0], st);
+          for (int64_t sg = 0; sg < bc; sg += SG) {
+            const int64_t nr = std::min(SG, bc - sg);
+            for (int64_t g = sg / RowTrimmer::GROUP; g * RowTrimmer::GROUP < sg + nr; ++g) trimmer->wait(g);
+            SPAI_CUDA(cudaMemcpyAsync(len_dev + sg, trimmer->len.data() + sg, (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+            bool fused = false;
+            SPAI_TRY(launch_k0(P, hdev + sg * ld, nr, T, ld, mask + sg * W, nnz0 + sg, len_dev + sg, st, &launches,
+                               &fused));
+            if (fused) nnz_ready = nnz0;
+          }
+          k0_done = true;
+        } else {
+          for (int64_t g = 0; g * RowTrimmer::GROUP < bc; ++g) {
+            trimmer->wait(g);
+            const int64_t hi = std::min(bc, (g + 1) * RowTrimmer::GROUP);
+            for (int64_t b = g * RowTrimmer::GROUP; b < hi; ++b) {
+              const int64_t n = trimmer->len[b];
+              if (n) SPAI_CUDA(cudaMemcpyAsync(buf + b * T, hbase + b * ld, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            }
+          }
+          SPAI_CUDA(cudaMemcpyAsync(len_dev, trimmer->len.data(), (size_t)bc * 4, cudaMemcpyHostToDevice, st));
+        }
         row_len_dev = len_dev;
         h2d_bytes += (double)bc * 4;
         for (int64_t b = 0; b < bc; ++b) h2d_bytes += 8.0 * trimmer->len[b];
@@ -958,7 +1022,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
       o_rw = reward ? reward + b0 : nullptr; o_rs = residual ? residual + b0 : nullptr;
       o_nz = nnz_m ? nnz_m + b0 : nullptr;
     }
-    if (pt->on) cudaEventRecord(pt->ev[0], st);
+    if (pt->on && !k0_done) cudaEventRecord(pt->ev[0], st);
     if (W > 0) {
       if (src == FROM_TAKEN_DEV) {
         const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
@@ -967,32 +1031,10 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
             P.E, mask, W, bc);
         SPAI_CUDA(cudaGetLastError()); ++launches;
       } else {
-        // variant: shared-memory bitmask per trajectory when it fits, else global RED
-        static const int k0_variant = [] {
-          const char* v = getenv("SPAI_K0_VARIANT");
-          return !v ? 0 : (!strcmp(v, "red") ? 1 : (!strcmp(v, "smem") ? 2 : 0));
-        }();
-        const bool fits = W * 4 <= K0S_MAX_SMEM;
-        if (fits && k0_variant != 1 && T > 0) {
-          SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         K0S_MAX_SMEM));
-          k0_mask_build_smem_kernel<<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(
-              act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nnz0, row_len_dev);
-          nnz_ready = nnz0;
-          SPAI_CUDA(cudaGetLastError()); ++launches;
-        } else {
-          const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
-          k0_mask_init_kernel<<<blocks, 256, 0, st>>>(mask, W, P.E, bc);
-          SPAI_CUDA(cudaGetLastError()); ++launches;
-          if (T > 0) {
-            constexpr int U = 4;
-            const int64_t chunks_t = ceil_div(T, 256 * U);
-            const int64_t nblk = chunks_t * bc;
-            if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
-            k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
-                act_dev, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t, row_len_dev);
-            SPAI_CUDA(cudaGetLastError()); ++launches;
-          }
+        if (!k0_done) {
+          bool fused = false;
+          SPAI_TRY(launch_k0(P, act_dev, bc, T, act_ld, mask, nnz0, row_len_dev, st, &launches, &fused));
+          if (fused) nnz_ready = nnz0;
         }
       }
     }
