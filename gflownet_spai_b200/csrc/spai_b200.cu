@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 #include <atomic>
+#include <chrono>
 #include <numeric>
 #include <thread>
 
