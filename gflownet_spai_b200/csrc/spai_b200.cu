@@ -924,7 +924,6 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   const int64_t W = P.words();
 
   // chunk size
-  const int64_t Bp_all = round_up(B, 32);
   int64_t Bc = B;
   auto need_for = [&](int64_t bc) {
     const int64_t bp = round_up(bc, 32);
@@ -937,7 +936,6 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   while (Bc > 32 && need_for(Bc) > c->ws_limit) Bc = std::max<int64_t>(32, round_up(Bc / 2, 32));
   const int64_t need = need_for(Bc);
   SPAI_TRY(c->ws.ensure(need));
-  (void)Bp_all;
 
   std::unique_ptr<RowTrimmer> trimmer;      // keeps the host length array alive until the stream is drained
   int64_t trimmer_b0 = -1;
