@@ -94,3 +94,30 @@ def test_full_size_cfg2_properties_and_spot_check():
     want64 = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val, p.a, acts[sel[:1]], 0.5, dtype=np.float64)
     np.testing.assert_allclose(cp["reward"].cpu().numpy()[:1], want64["reward"], rtol=1e-10, atol=1e-8)
     ctx.close()
+
+
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg4"])
+def test_full_size_cfg3_cfg4_spot_checks(cfg):
+    """BASELINE.json configs[2] and [3] at full size (n = 262 144): device and
+    host entry points agree, one pattern is re-scored by the oracle, the ls
+    residual never exceeds the copy residual, fp32 and fp64 agree to fp32 accuracy."""
+    p = synth.make_problem(cfg)
+    assert p.n == 262144
+    ctx = _ctx(p)
+    acts = synth.make_trajectories(p.num_edges, 6, seed0=300)
+    t = torch.from_numpy(acts)
+    dev32 = ctx.reward_batch(t.cuda(), 0.5, "copy", torch.float32)
+    host32 = ctx.reward_batch(t, 0.5, "copy", torch.float32)
+    assert torch.equal(dev32["reward"].cpu(), host32["reward"])
+    want = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val.astype(np.float32),
+                                 p.a.astype(np.float32), acts[:1], 0.5, dtype=np.float32)
+    np.testing.assert_allclose(dev32["reward"].cpu().numpy()[:1], want["reward"], rtol=1e-4, atol=2e-2)
+    assert int(dev32["nnz_m"][0]) == int(want["nnz_m"][0])
+    dev64 = ctx.reward_batch(t.cuda(), 0.5, "copy", torch.float64)
+    # same pattern, two precisions: residuals agree to fp32 accuracy (baselines differ per dtype)
+    assert torch.allclose(dev32["residual"], dev64["residual"], rtol=1e-5)
+    ls = ctx.reward_batch(t[:3].cuda(), 0.5, "ls", torch.float64)
+    assert torch.all(ls["residual"] <= dev64["residual"][:3] + 1e-9)
+    ls32 = ctx.reward_batch(t[:3].cuda(), 0.5, "ls", torch.float32)
+    assert torch.allclose(ls32["residual"], ls["residual"], rtol=1e-4)
+    ctx.close()
