@@ -24,7 +24,8 @@ EXPORTS = [
     "spai_ctx_destroy", "spai_ctx_info", "spai_ctx_set_workspace_limit",
     "spai_reward_batch_host", "spai_reward_batch_dev", "spai_kept_mask_dev",
     "spai_reward_from_taken_dev", "spai_row_index_sets", "spai_ls_solve_values_host",
-    "spai_residual_pair_host", "spai_sample_step_dev", "spai_pack_taken_dev", "spai_ctx_enable_timing",
+    "spai_residual_pair_host", "spai_sample_step_dev", "spai_pack_taken_dev", "spai_reward_rows_dev", "spai_finalize_rewards_dev",
+    "spai_ctx_enable_timing",
     "spai_ctx_last_timing",
 ]
 
@@ -86,6 +87,8 @@ def load():
     lib.spai_ls_solve_values_host.argtypes = [pv, pv, i64, i32, pv, pv]
     lib.spai_residual_pair_host.argtypes = [i32, i64, i64, pv, pv, pv, i64, pv, pv, pv, i32, pd, p64]
     lib.spai_sample_step_dev.argtypes = [pv, pv, i64, i64, pv, i64, pv, pv, i64, pv, pv, pv]
+    lib.spai_reward_rows_dev.argtypes = [pv, pv, i64, i64, i64, i32, i32, i64, i64, pv, pv, pv]
+    lib.spai_finalize_rewards_dev.argtypes = [pv, pv, pv, i64, dbl, i32, pv, pv, pv]
     lib.spai_pack_taken_dev.argtypes = [pv, pv, i64, i64, i64, pv, i64, pv, pv]
     lib.spai_ctx_enable_timing.argtypes = [pv, i32]
     lib.spai_ctx_last_timing.argtypes = [pv, C.POINTER(SpaiTiming)]

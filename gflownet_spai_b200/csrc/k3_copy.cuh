@@ -219,7 +219,7 @@ k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* 
                const RowHdr* __restrict__ rhdr, const T* __restrict__ row_base,
                const int32_t* __restrict__ tile_row, int ntiles,
                const uint32_t* __restrict__ maskT, int64_t Bp, int64_t W,
-               double* __restrict__ partial) {
+               double* __restrict__ partial, int row_lo, int row_hi) {
   using Rec = typename RecOf<T>::type;
   extern __shared__ __align__(128) unsigned char k3_smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(k3_smem);                    // 2 mbarriers
@@ -276,6 +276,7 @@ k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* 
     for (int i = 0; i < r1 - r0; ++i) {
       const RowHdr h = hdr[i];
       if (h.cnt == 0) continue;
+      if (r0 + i < row_lo || r0 + i >= row_hi) { off += h.cnt; continue; }     // row-range evaluation
       const bool fd = h.flags & 1;
       if (h.k <= 32) {
         const T base = row_base[r0 + i];
@@ -307,7 +308,8 @@ __global__ void k3_finalize_kernel(const double* __restrict__ partial, int npart
                                    double n, double res0, double flops0, double alpha,
                                    double* __restrict__ reward, double* __restrict__ residual,
                                    long long* __restrict__ nnz_out,
-                                   const unsigned int* __restrict__ fail_count, unsigned int fail_cap) {
+                                   const unsigned int* __restrict__ fail_count, unsigned int fail_cap,
+                                   int partial_only) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double s = rows_missing_diag;
@@ -315,8 +317,13 @@ __global__ void k3_finalize_kernel(const double* __restrict__ partial, int npart
   if (fail_count && *fail_count > fail_cap) s = __longlong_as_double(0x7ff8000000000000LL);
   for (int g = 0; g < nparts; ++g) s += partial[(int64_t)g * Bp + b];
   if (res2_extra) s += res2_extra[b];
-  const double res = sqrt(s);
   const long long z = nnz[b];
+  if (partial_only) {                 // row-range evaluation: the caller sums over ranks first
+    if (residual) residual[b] = s;
+    if (nnz_out) nnz_out[b] = z;
+    return;
+  }
+  const double res = sqrt(s);
   const double flops = 2.0 * (double)z * n;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const double rr = (res0 != 0.0) ? res / res0 : inf;

@@ -272,6 +272,7 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
   }
   if (tiles.back() != n) tiles.push_back((int32_t)n);
   plan.ntiles = (int)tiles.size() - 1;
+  plan.tile_row_host = tiles;
   SPAI_TRY(ar.upload(&plan.tile_row, tiles));
 
   std::vector<int32_t> cls[LS_NCLASS];
@@ -301,7 +302,10 @@ static int build_plan(Arena& ar, const Pattern& P, const HostPattern& hp, const 
     }
   }
   plan.g_bytes_full = g;
+  plan.missing_prefix.assign(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) plan.missing_prefix[i + 1] = plan.missing_prefix[i] + (hd[i] < 0 ? 1 : 0);
   for (int c = 0; c < LS_NCLASS; ++c) {
+    plan.class_rows_host[c] = cls[c];
     plan.class_count[c] = (int64_t)cls[c].size();
     if (want_ls && !cls[c].empty()) SPAI_TRY(ar.upload(&plan.class_rows[c], cls[c]));
   }
@@ -463,7 +467,7 @@ static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int d
 template <typename T>
 static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const EvalShape& s,
                            const uint32_t* maskT, int64_t Bp, int64_t Bc, double* partial, int2* fail_pairs,
-                           unsigned int* fail_count, cudaStream_t st) {
+                           unsigned int* fail_count, cudaStream_t st, int64_t roff, int64_t rcnt) {
   using Rec = typename RecOf<T>::type;
   const Rec* recs = reinterpret_cast<const Rec*>(plan.rec_ls);
   const dim3 grid(s.ls_gx[c], s.ls_gy[c]);
@@ -471,13 +475,13 @@ static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const Eval
 #define SPAI_LS_ROW(IDX, KMAX, G, QL)                                                          \
   case IDX:                                                                                    \
     k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
-        plan.class_rows[c], plan.class_count[c], maskT, Bp, s.ls_ntg[c], partial,              \
+        plan.class_rows[c] + roff, rcnt, maskT, Bp, s.ls_ntg[c], partial,                       \
         plan.row_base_ls);                                                                     \
     break;
 #define SPAI_LS_COL(IDX, W, QMAX)                                                              \
   case IDX:                                                                                    \
     k2c_ls_kernel<T, W, QMAX><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,     \
-        plan.class_rows[c], plan.class_count[c], maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs, \
+        plan.class_rows[c] + roff, rcnt, maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs,       \
         fail_count, LS_FAIL_CAP, plan.row_base_ls);                                            \
     break;
   switch (c) {
@@ -511,8 +515,19 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
                       int64_t Bc, char* scratch, int64_t scratch_bytes, int sm_count, double n_d,
                       double res0, double flops0, double alpha, double* reward, double* residual,
                       int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches,
-                      const long long* nnz_ready = nullptr) {
+                      const long long* nnz_ready = nullptr, int64_t row_lo = 0, int64_t row_hi = -1,
+                      bool partial_only = false) {
   const int64_t W = P.words();
+  if (row_hi < 0 || row_hi > plan.n) row_hi = plan.n;
+  if (row_lo < 0) row_lo = 0;
+  if (row_lo > row_hi) row_lo = row_hi;
+  // sub-range of a sorted class row list
+  auto sub = [&](int c, int64_t* off, int64_t* cnt) {
+    const auto& v = plan.class_rows_host[c];
+    const int64_t a = std::lower_bound(v.begin(), v.end(), (int32_t)row_lo) - v.begin();
+    const int64_t b = std::lower_bound(v.begin(), v.end(), (int32_t)std::min<int64_t>(row_hi, INT32_MAX)) - v.begin();
+    *off = a; *cnt = b - a;
+  };
   const EvalShape s = plan_shape(plan, mode, dtype, Bc, sm_count);
   const int64_t Bp = s.Bp;
   Carver cv{scratch, scratch + scratch_bytes};
@@ -546,11 +561,22 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   if (mode == SPAI_MODE_COPY) {
     const dim3 grid(s.gx, s.gy);
     const size_t smem = (size_t)K3_SMEM_BYTES;
+    // tiles that intersect [row_lo, row_hi)
+    const auto& tr = plan.tile_row_host;
+    int t_lo = 0, t_n = plan.ntiles;
+    if (row_lo > 0 || row_hi < plan.n) {
+      t_lo = (int)(std::upper_bound(tr.begin(), tr.end(), (int32_t)row_lo) - tr.begin()) - 1;
+      int t_hi = (int)(std::lower_bound(tr.begin(), tr.end(), (int32_t)row_hi) - tr.begin());
+      t_lo = std::max(0, std::min(t_lo, plan.ntiles));
+      t_hi = std::max(t_lo, std::min(t_hi, plan.ntiles));
+      t_n = (row_hi > row_lo) ? t_hi - t_lo : 0;
+    }
 #define SPAI_K3(T, NT)                                                                          \
   k3_copy_kernel<T, NT><<<grid, K3_THREADS, smem, st>>>(                                        \
       reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, plan.rhdr,    \
-      reinterpret_cast<const T*>(plan.row_base), plan.tile_row, plan.ntiles, maskT, Bp, W, partial)
-    if (plan.ntiles == 0) {
+      reinterpret_cast<const T*>(plan.row_base), plan.tile_row + t_lo, t_n, maskT, Bp, W, partial,  \
+      (int)row_lo, (int)row_hi)
+    if (t_n == 0) {
       SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)s.parts * Bp * 8, st));
     } else if (dtype == SPAI_F32) {
       if (s.nt == 8) SPAI_K3(float, 8); else if (s.nt == 4) SPAI_K3(float, 4);
@@ -581,10 +607,12 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
       if (!plan.class_count[c]) continue;
       double* pp = partial + (int64_t)off * Bp;
+      int64_t roff, rcnt;
+      sub(c, &roff, &rcnt);
       if (dtype == SPAI_F32)
-        SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st));
+        SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
       else
-        SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st));
+        SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
       off += s.ls_gx[c]; ++nl; any = true;
     }
     if (!any) { SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); parts = 1; }
@@ -596,16 +624,19 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
         if (pass == 0 && !plan.class_count[LS_GENERIC]) continue;
         if (pass == 1 && !s.has_column_class) continue;
         const int2* pairs = pass ? fail_pairs : nullptr;
+        int64_t goff = 0, gcnt = plan.class_count[LS_GENERIC];
+        if (!pass) sub(LS_GENERIC, &goff, &gcnt);
+        const int32_t* grows = plan.class_rows[LS_GENERIC] ? plan.class_rows[LS_GENERIC] + goff : nullptr;
         if (dtype == SPAI_F32)
           k2_ls_generic_kernel<float><<<blocks, 128, 0, st>>>(
               reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
-              plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
+              grows, gcnt, maskT, Bp, Bc,
               reinterpret_cast<float*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
               LS_FAIL_CAP, nullptr);
         else
           k2_ls_generic_kernel<double><<<blocks, 128, 0, st>>>(
               reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
-              plan.class_rows[LS_GENERIC], plan.class_count[LS_GENERIC], maskT, Bp, Bc,
+              grows, gcnt, maskT, Bp, Bc,
               reinterpret_cast<double*>(gwork), s.generic_work, cmap, s.generic_cmap, res2x, pairs, fail_count,
               LS_FAIL_CAP, nullptr);
         SPAI_CUDA(cudaGetLastError()); ++nl;
@@ -614,8 +645,11 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   }
   if (pt && pt->on) cudaEventRecord(pt->ev[3], st);
   k3_finalize_kernel<<<(unsigned)ceil_div(Bc, 256), 256, 0, st>>>(
-      partial, parts, Bp, Bc, use_extra ? res2x : nullptr, (double)plan.rows_missing_diag, nnz, n_d,
-      res0, flops0, alpha, reward, residual, reinterpret_cast<long long*>(nnz_out), fail_count_dev, LS_FAIL_CAP);
+      partial, parts, Bp, Bc, use_extra ? res2x : nullptr,
+      (double)(plan.missing_prefix.empty() ? plan.rows_missing_diag
+                                           : plan.missing_prefix[row_hi] - plan.missing_prefix[row_lo]),
+      nnz, n_d, res0, flops0, alpha, reward, residual, reinterpret_cast<long long*>(nnz_out), fail_count_dev,
+      LS_FAIL_CAP, partial_only ? 1 : 0);
   SPAI_CUDA(cudaGetLastError()); ++nl;
   if (launches) *launches += nl;
   return SPAI_OK;
@@ -645,6 +679,8 @@ struct spai_ctx {
   Workspace ws;
   PhaseTimer pt;
   spai_timing last = {};
+  int64_t row_lo = 0, row_hi = -1;      // row-range evaluation (spai_reward_rows_dev), reset after the call
+  bool partial_only = false;
 };
 
 namespace spai {
@@ -1051,7 +1087,8 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     char* scratch = cv.take<char>(0);
     const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
     SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
-                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready));
+                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready, c->row_lo,
+                        c->row_hi, c->partial_only));
     if (pt->on) cudaEventRecord(pt->ev[4], st);
     if (out_host) {
       if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
@@ -1222,6 +1259,35 @@ int spai_sample_step_dev(spai_ctx* c, const float* logits, int64_t logits_ld, in
   DeviceGuard guard(c->device);
   k4_sample_kernel<<<(unsigned)B, K4_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       logits, logits_ld, A, taken, words_ld, uniforms, done, action, prob);
+  SPAI_CUDA(cudaGetLastError());
+  return SPAI_OK;
+}
+
+int spai_reward_rows_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld, int mode,
+                         int dtype, int64_t row_begin, int64_t row_end, double* res2_partial, int64_t* nnz_m,
+                         void* stream) {
+  if (!c || row_begin < 0 || row_end < row_begin || row_end > c->n || !res2_partial) {
+    set_error("spai_reward_rows_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  c->row_lo = row_begin; c->row_hi = row_end; c->partial_only = true;
+  const int st = reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, 0.5, mode, dtype, nullptr, res2_partial,
+                               nnz_m, false, nullptr, stream);
+  c->row_lo = 0; c->row_hi = -1; c->partial_only = false;
+  return st;
+}
+
+int spai_finalize_rewards_dev(spai_ctx* c, const double* res2, const int64_t* nnz_m, int64_t B, double alpha,
+                              int dtype, double* reward, double* residual, void* stream) {
+  if (!c || B < 0 || (B && (!res2 || !nnz_m)) || (dtype != SPAI_F32 && dtype != SPAI_F64)) {
+    set_error("spai_finalize_rewards_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  if (B == 0) return SPAI_OK;
+  DeviceGuard guard(c->device);
+  k3_finalize_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      res2, 1, B, B, nullptr, 0.0, reinterpret_cast<const long long*>(nnz_m), (double)c->n, c->res0[dtype],
+      (double)c->flops0, alpha, reward, residual, nullptr, nullptr, 0u, 0);
   SPAI_CUDA(cudaGetLastError());
   return SPAI_OK;
 }

@@ -126,10 +126,13 @@ struct Plan {
   int max_k = 0;
   // copy-kernel tiling: tile t = rows [tile_row[t], tile_row[t+1])
   int32_t* tile_row = nullptr;    // [ntiles+1] device
+  std::vector<int32_t> tile_row_host;
   int ntiles = 0;
   // ls-kernel row classes
   int32_t* class_rows[LS_NCLASS] = {};
   int64_t class_count[LS_NCLASS] = {};
+  std::vector<int32_t> class_rows_host[LS_NCLASS];   // sorted ascending (row-range evaluation)
+  std::vector<int64_t> missing_prefix;               // [n+1] prefix count of rows without a diagonal slot
   int64_t generic_max_q = 0, generic_max_k = 0;
   double g_bytes_full = 0;        // SURVEY §8d G with every candidate kept (bytes / pattern)
   int64_t bytes = 0;

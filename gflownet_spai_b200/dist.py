@@ -47,3 +47,18 @@ def gather_rewards(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
     out = torch.empty(world * width, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
+
+def reward_row_sharded(ctx, actions: torch.Tensor, alpha: float, mode: str = "copy",
+                       dtype: torch.dtype = torch.float32, group=None):
+    """Secondary partitioning (few trajectories, huge n): every rank evaluates the
+    rows [lo, hi) = shard_bounds(n, world, rank) of EVERY trajectory; the partial
+    sums of squared row residuals are all-reduced (one f64[B] sum) before the sqrt
+    and the mix formula. `actions` is the full CUDA int64 [B, T] batch on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(ctx.n, world, rank)
+    res2, nnz = ctx.reward_rows(actions, lo, hi, mode, dtype)
+    if world > 1:
+        dist.all_reduce(res2, op=dist.ReduceOp.SUM, group=group)
+    return ctx.finalize_rewards(res2, nnz, alpha, dtype)

@@ -159,6 +159,32 @@ class SpaiContext:
                  _ptr(out["residual"]), _ptr(out["nnz_m"]), self._stream()), "spai_reward_batch")
         return {k: v for k, v in out.items() if v is not None}
 
+    def reward_rows(self, actions: torch.Tensor, row_begin: int, row_end: int, mode: str = "copy",
+                    dtype: torch.dtype = torch.float32):
+        """Partial evaluation of rows [row_begin, row_end) (row sharding across GPUs):
+        (sum of squared row residuals f64[B], nnz(M) i64[B]) for CUDA `actions`."""
+        if not actions.is_cuda or actions.dtype != torch.int64 or actions.dim() != 2:
+            raise ValueError("actions must be a CUDA int64 [B, T] tensor")
+        actions = actions.contiguous()
+        b, t = actions.shape
+        res2 = torch.empty(b, dtype=torch.float64, device=actions.device)
+        nnz = torch.empty(b, dtype=torch.int64, device=actions.device)
+        check(self._lib.spai_reward_rows_dev(self._h, _ptr(actions), b, t, max(t, 1), MODES[mode],
+                                             F32 if dtype == torch.float32 else F64, int(row_begin), int(row_end),
+                                             _ptr(res2), _ptr(nnz), self._stream()), "spai_reward_rows_dev")
+        return res2, nnz
+
+    def finalize_rewards(self, res2: torch.Tensor, nnz: torch.Tensor, alpha: float,
+                         dtype: torch.dtype = torch.float32):
+        """sqrt + mix formula on summed partials (see reward_rows)."""
+        b = res2.numel()
+        reward = torch.empty(b, dtype=torch.float64, device=res2.device)
+        residual = torch.empty_like(reward)
+        check(self._lib.spai_finalize_rewards_dev(self._h, _ptr(res2), _ptr(nnz), b, float(alpha),
+                                                  F32 if dtype == torch.float32 else F64, _ptr(reward),
+                                                  _ptr(residual), self._stream()), "spai_finalize_rewards_dev")
+        return {"reward": reward, "residual": residual, "nnz_m": nnz}
+
     def reward_from_taken(self, taken: torch.Tensor, alpha: float, mode: str = "copy",
                           dtype: torch.dtype = torch.float32):
         """taken int32[B, words] CUDA tensor, EDGE order, bit set = edge removed."""

@@ -156,6 +156,19 @@ int spai_sample_step_dev(spai_ctx* ctx, const float* logits_dev, int64_t logits_
                          uint8_t* done_dev, int64_t B, int64_t* action_dev, float* prob_dev,
                          void* stream);
 
+/* Secondary partitioning across GPUs: evaluate only rows
+ * [row_begin, row_end) of M for every trajectory. res2_partial_dev f64[B] receives the
+ * sum of squared row residuals of that range (no sqrt, no mix; rows of the range
+ * whose union misses the diagonal included), nnz_m_dev i64[B] the full nnz(M).
+ * Sum res2 over the ranks (all-reduce), then spai_finalize_rewards_dev applies
+ * sqrt and the mix formula (preconditioner.py:154-163, :64). */
+int spai_reward_rows_dev(spai_ctx* ctx, const int64_t* actions_dev, int64_t B, int64_t T, int64_t ld,
+                         int mode, int dtype, int64_t row_begin, int64_t row_end,
+                         double* res2_partial_dev, int64_t* nnz_m_dev, void* stream);
+int spai_finalize_rewards_dev(spai_ctx* ctx, const double* res2_dev, const int64_t* nnz_m_dev, int64_t B,
+                              double alpha, int dtype, double* reward_dev, double* residual_dev,
+                              void* stream);
+
 /* Whole-trajectory sampling support (Gumbel-top-k; equal in distribution to the
  * step-by-step masked categorical draws of gflownet.py:135-179): given perturbed
  * keys f32[B, keys_ld] (logit + Gumbel noise, column A-1 = terminal), writes the

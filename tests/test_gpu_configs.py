@@ -121,3 +121,29 @@ def test_full_size_cfg3_cfg4_spot_checks(cfg):
     ls32 = ctx.reward_batch(t[:3].cuda(), 0.5, "ls", torch.float32)
     assert torch.allclose(ls32["residual"], ls["residual"], rtol=1e-4)
     ctx.close()
+
+
+@pytest.mark.parametrize("mode,dtype,tol", [("copy", torch.float32, 1e-6), ("copy", torch.float64, 1e-12),
+                                            ("ls", torch.float64, 1e-12)])
+def test_row_range_partials_sum_to_the_full_reward(mode, dtype, tol):
+    """Row sharding (secondary): partial sums over disjoint row ranges,
+    added and finalised, equal the full evaluation (emulates 3 ranks on one GPU)."""
+    from gflownet_spai_b200.dist import shard_bounds, reward_row_sharded
+    p = synth.make_problem("cfg5", 0.004)                 # n = 4000, mixed ls classes incl. generic rows
+    ctx = _ctx(p)
+    acts = torch.from_numpy(synth.make_trajectories(p.num_edges, 9, seed0=4)).cuda()
+    full = ctx.reward_batch(acts, 0.3, mode, dtype)
+    tot = torch.zeros(9, dtype=torch.float64, device="cuda")
+    for r in range(3):
+        lo, hi = shard_bounds(p.n, 3, r)
+        part, nnz = ctx.reward_rows(acts, lo, hi, mode, dtype)
+        tot += part
+        assert torch.equal(nnz, full["nnz_m"])
+    fin = ctx.finalize_rewards(tot, nnz, 0.3, dtype)
+    assert torch.allclose(fin["residual"], full["residual"], rtol=tol, atol=1e-12)
+    assert torch.allclose(fin["reward"], full["reward"], rtol=tol, atol=1e-6)
+    one = reward_row_sharded(ctx, acts, 0.3, mode, dtype)                       # world size 1 path
+    assert torch.allclose(one["reward"], full["reward"], rtol=tol, atol=1e-6)
+    empty, _ = ctx.reward_rows(acts, 17, 17, mode, dtype)
+    assert float(empty.abs().max()) == 0.0
+    ctx.close()
