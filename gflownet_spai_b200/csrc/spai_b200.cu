@@ -182,8 +182,8 @@ static int upload_csr(Arena& ar, const HostCsr& h, int64_t n, int64_t stored, Cs
 //   kind 1: column-per-lane tile (k2c_ls_kernel<T,W,QMAX>), W = KMAX lanes per problem
 struct LsClass { int kind, kmax, g, ql; };
 static const LsClass kLsClasses[LS_NCLASS - 1] = {
-    {0, 8, 4, 5}, {0, 8, 8, 5}, {1, 16, 16, 52}, {1, 16, 16, 64},
-    {1, 32, 32, 52}, {1, 32, 32, 64}, {0, 0, 0, 0}};
+    {0, 8, 2, 9}, {0, 8, 4, 5}, {0, 8, 8, 5}, {1, 16, 16, 52}, {1, 16, 16, 64},
+    {1, 32, 32, 52}, {1, 32, 32, 64}};
 static inline int ls_class_rows_max(const LsClass& L) { return L.kind == 0 ? L.g * L.ql : L.ql; }
 static inline int ls_class_lanes(const LsClass& L) { return L.g; }
 
@@ -485,12 +485,13 @@ static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const Eval
         fail_count, LS_FAIL_CAP, plan.row_base_ls);                                            \
     break;
   switch (c) {
-    SPAI_LS_ROW(0, 8, 4, 5)
-    SPAI_LS_ROW(1, 8, 8, 5)
-    SPAI_LS_COL(2, 16, 52)
-    SPAI_LS_COL(3, 16, 64)
-    SPAI_LS_COL(4, 32, 52)
-    SPAI_LS_COL(5, 32, 64)
+    SPAI_LS_ROW(0, 8, 2, 9)
+    SPAI_LS_ROW(1, 8, 4, 5)
+    SPAI_LS_ROW(2, 8, 8, 5)
+    SPAI_LS_COL(3, 16, 52)
+    SPAI_LS_COL(4, 16, 64)
+    SPAI_LS_COL(5, 32, 52)
+    SPAI_LS_COL(6, 32, 64)
     default: set_error("bad ls class %d", c); return SPAI_ERR_INVALID;
   }
 #undef SPAI_LS_ROW

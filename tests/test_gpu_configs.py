@@ -18,9 +18,9 @@ def _ctx(p):
 
 
 @pytest.mark.parametrize("cfg,scale,ls_class", [
-    ("cfg2", 0.125, 0),      # 32x32 grid, k<=8,  |I|<=18  -> (8,4,5)
-    ("cfg3", 0.1875, 2),     # 12^3 grid,  k<=16, |I|<=45  -> (16,16,3)
-    ("cfg4", 0.046875, 4),   # 24x24 grid, k<=32, |I|<=50  -> (32,32,2)
+    ("cfg2", 0.125, 0),      # 32x32 grid, k<=8,  |I|<=18  -> row kernel (8,2,9)
+    ("cfg3", 0.1875, 3),     # 12^3 grid,  k<=16, |I|<=49  -> column kernel W=16, QMAX=52
+    ("cfg4", 0.046875, 5),   # 24x24 grid, k<=32, |I|<=50  -> column kernel W=32, QMAX=52
     ("cfg5", 0.0015, None),  # n=1500 banded + power law: mixed classes incl. generic
 ])
 def test_scaled_configs_match_oracle(cfg, scale, ls_class):

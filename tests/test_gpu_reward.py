@@ -332,7 +332,7 @@ def test_rank_deficient_tiles_are_handed_to_the_generic_kernel():
     from gflownet_spai_b200.env import SpaiContext
     ctx = SpaiContext(n, r, c, v, coo.row, coo.col, coo.data)
     info = ctx.info()
-    assert info.ls_class_rows[2] + info.ls_class_rows[3] > 0        # column-per-lane classes in use
+    assert info.ls_class_rows[3] + info.ls_class_rows[4] > 0        # column-per-lane classes in use
     acts = synth.make_trajectories(r.size, 6, seed0=2, max_frac=0.2)
     acts[0, :] = -1                                                  # everything kept: rows 0,3,6.. are deficient
     want = orc.reward_batch_ls(n, r, c, a, acts, 0.5, dtype=np.float64, baseline_dtype=np.float64)
