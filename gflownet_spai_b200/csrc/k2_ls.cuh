@@ -55,60 +55,63 @@ __device__ __forceinline__ double k2_rcp(double x) { return __drcp_rn(x); }
 // the largest number of kept columns among the problems of this warp: the kept
 // columns are compacted to the front when the tile is loaded, so steps and
 // trailing columns >= kkw are all-zero for every lane and are skipped with
-// warp-uniform branches.
+// warp-uniform branches. Full column rank is assumed, i.e. the pivot row of step
+// E is row E: "row r >= E" is then a compile-time fact for all but the one
+// register row that straddles E (rows are dealt cyclically, r = t*G + lg), which
+// removed ~half of the issued instructions (64-bit selects on a runtime pivot).
+// A tile that turns out rank-deficient sets `bad` and is redone by the generic
+// kernel (same hand-over list as the column kernel).
 template <typename T, int KMAX, int G, int QL, int E>
-__device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], int& p, T (&cn2)[KMAX],
-                                        int lg, int kkw) {
+__device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], T (&cn2)[KMAX], int lg, int kk,
+                                        int kkw, bool& bad) {
   if (E >= kkw) return;
-  T sig = T(0), alp = T(0);
+  constexpr int TB = E / G;                 // register row that holds matrix row E (on lane E % G)
+  constexpr int LB = E % G;
+  if constexpr (TB < QL) {
+    // ||a[E:, E]||^2 : rows t > TB are below the pivot on every lane, row TB only on lanes >= LB
+    T sig = (lg >= LB) ? a[TB][E] * a[TB][E] : T(0);
 #pragma unroll
-  for (int t = 0; t < QL; ++t) {
-    const int r = t * G + lg;
-    const T v = (r >= p) ? a[t][E] : T(0);
-    sig = fma(v, v, sig);
-    alp = (r == p) ? v : alp;
-  }
-  sig = k2_gsum<G>(sig);
-  alp = k2_gsum<G>(alp);
-  const bool act = sig > cn2[E] * K2Tol<T>::v;
-  const T sg = act ? sig : T(1);
-  const T nrm = sg * k2_rsqrt(sg);
-  const T beta = (alp >= T(0)) ? -nrm : nrm;
-  const T inv = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
-  T vt[QL];
+    for (int t = TB + 1; t < QL; ++t) sig = fma(a[t][E], a[t][E], sig);
+    sig = k2_gsum<G>(sig);
+    const T alp = __shfl_sync(0xffffffffu, a[TB][E], LB, G);          // pivot element a[E][E]
+    const bool act = sig > cn2[E] * K2Tol<T>::v;
+    const T sg = act ? sig : T(1);
+    const T nrm = sg * k2_rsqrt(sg);
+    const T beta = (alp >= T(0)) ? -nrm : nrm;
+    const T inv = act ? k2_rcp(fma(-alp, beta, sg)) : T(0);
+    bad |= (E < kk) && !act;
+    // v: row E -> alp - beta, rows > E -> a[.,E], rows < E -> 0 (only register row TB is lane-dependent)
+    const T vb = (lg > LB) ? a[TB][E] : ((lg == LB) ? alp - beta : T(0));
 #pragma unroll
-  for (int t = 0; t < QL; ++t) {
-    const int r = t * G + lg;
-    vt[t] = (r > p) ? a[t][E] : ((r == p) ? alp - beta : T(0));
-  }
+    for (int c = E + 1; c < KMAX; ++c) {
+      if (c < kkw) {
+        T dot = vb * a[TB][c];
 #pragma unroll
-  for (int c = E + 1; c < KMAX; ++c) {
-    if (c < kkw) {
-      T dot = T(0);
+        for (int t = TB + 1; t < QL; ++t) dot = fma(a[t][E], a[t][c], dot);
+        dot = k2_gsum<G>(dot);
+        const T f = dot * inv;
+        a[TB][c] = fma(-f, vb, a[TB][c]);
 #pragma unroll
-      for (int t = 0; t < QL; ++t) dot = fma(vt[t], a[t][c], dot);
+        for (int t = TB + 1; t < QL; ++t) a[t][c] = fma(-f, a[t][E], a[t][c]);
+      }
+    }
+    {
+      T dot = vb * y[TB];
+#pragma unroll
+      for (int t = TB + 1; t < QL; ++t) dot = fma(a[t][E], y[t], dot);
       dot = k2_gsum<G>(dot);
       const T f = dot * inv;
+      y[TB] = fma(-f, vb, y[TB]);
 #pragma unroll
-      for (int t = 0; t < QL; ++t) a[t][c] = fma(-f, vt[t], a[t][c]);
+      for (int t = TB + 1; t < QL; ++t) y[t] = fma(-f, a[t][E], y[t]);
     }
   }
-  {
-    T dot = T(0);
-#pragma unroll
-    for (int t = 0; t < QL; ++t) dot = fma(vt[t], y[t], dot);
-    dot = k2_gsum<G>(dot);
-    const T f = dot * inv;
-#pragma unroll
-    for (int t = 0; t < QL; ++t) y[t] = fma(-f, vt[t], y[t]);
-  }
-  p += act ? 1 : 0;
 }
 
 template <typename T, int KMAX, int G, int QL, int... Es>
-__device__ __forceinline__ void k2_all_steps(T (&a)[QL][KMAX], T (&y)[QL], int& p, T (&cn2)[KMAX],
-                                             int lg, int kkw, std::integer_sequence<int, Es...>) {
-  (k2_step<T, KMAX, G, QL, Es>(a, y, p, cn2, lg, kkw), ...);
+__device__ __forceinline__ void k2_all_steps(T (&a)[QL][KMAX], T (&y)[QL], T (&cn2)[KMAX], int lg, int kk,
+                                             int kkw, bool& bad, std::integer_sequence<int, Es...>) {
+  (k2_step<T, KMAX, G, QL, Es>(a, y, cn2, lg, kk, kkw, bad), ...);
 }
 
 constexpr int K2_NW = 4;          // warps per block
@@ -119,7 +122,9 @@ __global__ void __launch_bounds__(K2_NW * 32)
 k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
              const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
              const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
-             int64_t Bp, int ntg, double* __restrict__ partial, const double* __restrict__ row_base) {
+             int64_t Bp, int ntg, double* __restrict__ partial, const double* __restrict__ row_base,
+             int64_t B, int2* __restrict__ fail_pairs, unsigned int* __restrict__ fail_count,
+             unsigned int fail_cap) {
   using Rec = typename RecOf<T>::type;
   constexpr int QP = QL * G;
   constexpr int NG = 32 / G;
@@ -167,8 +172,8 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
 
 #pragma unroll 1
     for (int j = 0; j < ntg; ++j) {
-      int64_t b = bbase + (int64_t)j * GROUPS + gid;
-      if (b >= Bp) b = 0;                       // result discarded below
+      const int64_t breal = bbase + (int64_t)j * GROUPS + gid;
+      const int64_t b = (breal < Bp) ? breal : 0;           // result discarded below
       const uint32_t lo = maskT[w0 * Bp + b];
       const uint32_t hi = two ? maskT[(w0 + 1) * Bp + b] : 0u;
       const uint32_t m = __funnelshift_r(lo, hi, sh) & kmask;
@@ -193,17 +198,25 @@ k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __
       }
 #pragma unroll
       for (int t = 0; t < QL; ++t) y[t] = ((t * G + lg) == diag) ? T(1) : T(0);
-      const int kkw = __reduce_max_sync(0xffffffffu, __popc(m));
-      int p = 0;
-      k2_all_steps<T, KMAX, G, QL>(a, y, p, cn2, lg, kkw, std::make_integer_sequence<int, KMAX>{});
+      const int kk = __popc(m);
+      const int kkw = __reduce_max_sync(0xffffffffu, kk);
+      bool bad = false;
+      k2_all_steps<T, KMAX, G, QL>(a, y, cn2, lg, kk, kkw, bad, std::make_integer_sequence<int, KMAX>{});
       T r2 = T(0);
 #pragma unroll
       for (int t = 0; t < QL; ++t) {
         const int r = t * G + lg;
-        r2 += (r >= p) ? y[t] * y[t] : T(0);
+        r2 += (r >= kk) ? y[t] * y[t] : T(0);               // full rank: the first kk rows are eliminated
       }
       r2 = k2_gsum<G>(r2);
-      if (lg == 0) totsm[j * GROUPS + gid] += (double)r2;
+      if (lg == 0) {
+        if (bad && breal < B) {                              // rank-deficient tile: redone by the generic kernel
+          const unsigned int slot = atomicAdd(fail_count, 1u);
+          if (slot < fail_cap) fail_pairs[slot] = make_int2(i, (int)breal);
+          r2 = T(0);
+        }
+        totsm[j * GROUPS + gid] += (double)r2;
+      }
     }
   }
   __syncthreads();

@@ -191,7 +191,7 @@ static int classify_row(int k, int q, bool has_dup) {
   for (int c = 0; c < LS_NCLASS - 1; ++c) {
     const LsClass& L = kLsClasses[c];
     if (L.kmax == 0) continue;
-    if (L.kind == 1 && has_dup) continue;        // column kernel assumes full column rank
+    if (has_dup) continue;                        // register kernels assume full column rank
     if (k <= L.kmax && q <= ls_class_rows_max(L)) return c;
   }
   return LS_GENERIC;
@@ -430,7 +430,7 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
       if (!plan.class_count[c]) continue;
       const LsClass& L = kLsClasses[c];
       const int groups = K2_NW * (32 / ls_class_lanes(L));
-      if (L.kind == 1) s.has_column_class = true;
+      s.has_column_class = true;      // every register kernel assumes full rank and may hand tiles over
       s.ls_ntg[c] = (int)std::min<int64_t>(K2_MAX_NTG, ceil_div(Bp, groups));
       s.ls_gy[c] = (int)ceil_div(Bp, (int64_t)groups * s.ls_ntg[c]);
       const int target = sm_count * 12;
@@ -476,7 +476,7 @@ static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const Eval
   case IDX:                                                                                    \
     k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
         plan.class_rows[c] + roff, rcnt, maskT, Bp, s.ls_ntg[c], partial,                       \
-        plan.row_base_ls);                                                                     \
+        plan.row_base_ls, Bc, fail_pairs, fail_count, LS_FAIL_CAP);                            \
     break;
 #define SPAI_LS_COL(IDX, W, QMAX)                                                              \
   case IDX:                                                                                    \
