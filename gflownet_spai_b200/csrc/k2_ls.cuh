@@ -70,9 +70,12 @@ __device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], T (&cn2)[K
   if constexpr (TB < QL) {
     // ||a[E:, E]||^2 : rows t > TB are below the pivot on every lane, row TB only on lanes >= LB
     T sig = (lg >= LB) ? a[TB][E] * a[TB][E] : T(0);
+    T sig1 = T(0);                            // two chains: FMA latency binds at this occupancy
 #pragma unroll
-    for (int t = TB + 1; t < QL; ++t) sig = fma(a[t][E], a[t][E], sig);
-    sig = k2_gsum<G>(sig);
+    for (int t = TB + 1; t < QL; ++t) {
+      if ((t - TB) & 1) sig1 = fma(a[t][E], a[t][E], sig1); else sig = fma(a[t][E], a[t][E], sig);
+    }
+    sig = k2_gsum<G>(sig + sig1);
     const T alp = __shfl_sync(0xffffffffu, a[TB][E], LB, G);          // pivot element a[E][E]
     const bool act = sig > cn2[E] * K2Tol<T>::v;
     const T sg = act ? sig : T(1);
@@ -86,9 +89,12 @@ __device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], T (&cn2)[K
     for (int c = E + 1; c < KMAX; ++c) {
       if (c < kkw) {
         T dot = vb * a[TB][c];
+        T dot1 = T(0);
 #pragma unroll
-        for (int t = TB + 1; t < QL; ++t) dot = fma(a[t][E], a[t][c], dot);
-        dot = k2_gsum<G>(dot);
+        for (int t = TB + 1; t < QL; ++t) {
+          if ((t - TB) & 1) dot1 = fma(a[t][E], a[t][c], dot1); else dot = fma(a[t][E], a[t][c], dot);
+        }
+        dot = k2_gsum<G>(dot + dot1);
         const T f = dot * inv;
         a[TB][c] = fma(-f, vb, a[TB][c]);
 #pragma unroll
@@ -97,9 +103,12 @@ __device__ __forceinline__ void k2_step(T (&a)[QL][KMAX], T (&y)[QL], T (&cn2)[K
     }
     {
       T dot = vb * y[TB];
+      T dot1 = T(0);
 #pragma unroll
-      for (int t = TB + 1; t < QL; ++t) dot = fma(a[t][E], y[t], dot);
-      dot = k2_gsum<G>(dot);
+      for (int t = TB + 1; t < QL; ++t) {
+        if ((t - TB) & 1) dot1 = fma(a[t][E], y[t], dot1); else dot = fma(a[t][E], y[t], dot);
+      }
+      dot = k2_gsum<G>(dot + dot1);
       const T f = dot * inv;
       y[TB] = fma(-f, vb, y[TB]);
 #pragma unroll
