@@ -127,7 +127,10 @@ constexpr int K2_NW = 4;          // warps per block
 constexpr int K2_MAX_NTG = 16;    // trajectories per lane group
 
 template <typename T, int KMAX, int G, int QL>
-__global__ void __launch_bounds__(K2_NW * 32)
+// fp64, G = 2: 204 registers allow 2 CTAs/SM and the kernel is latency-bound (ncu: 12 % warps
+// active, stall = wait); capping at 168 registers (3 CTAs/SM, ~200 B of spills) is 1.25x faster,
+// 128 registers (4 CTAs/SM) spills ~1 KB and is slower again.
+__global__ void __launch_bounds__(K2_NW * 32, (sizeof(T) == 8 && G == 2) ? 3 : 1)
 k2_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
              const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
              const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
@@ -300,7 +303,7 @@ __device__ __forceinline__ void k2c_step(T (&a)[QMAX], T cn, T* __restrict__ vb,
 }
 
 template <typename T, int W, int QMAX>
-__global__ void __launch_bounds__(K2_NW * 32)
+__global__ void __launch_bounds__(K2_NW * 32)          // (forcing 3 CTAs/SM for fp64 spilled the column: 1.9x slower)
 k2c_ls_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
               const int32_t* __restrict__ sptr, const int32_t* __restrict__ r_diag,
               const int32_t* __restrict__ rows, int64_t nrows, const uint32_t* __restrict__ maskT,
