@@ -106,7 +106,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def stop(self):
         if self._thread is not None:
@@ -558,6 +558,7 @@ def run_b200_arm(args):
 
 
 def main():
+    sys.setswitchinterval(2e-4)         # let the clock-sampling thread run between the timed launches
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
