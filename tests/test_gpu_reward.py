@@ -375,3 +375,52 @@ def test_short_trajectories_take_the_untouched_row_path():
     gls32 = ctx.reward_batch(t, 0.5, "ls", torch.float32)
     np.testing.assert_allclose(gls32["residual"].cpu().numpy()[:5], wls["residual"], rtol=1e-4)
     ctx.close()
+
+
+def test_degenerate_shapes():
+    """n = 1, an empty initial matrix (E = 0), empty rows of A, B = 1 and T = 1."""
+    from gflownet_spai_b200.env import SpaiContext
+    one = np.array([0], dtype=np.int64)
+    ctx = SpaiContext(1, one, one, np.array([2.0]), one, one, np.array([3.0]))
+    out = ctx.reward_batch(torch.tensor([[1], [0]], dtype=torch.int64).cuda(), 0.5, "copy", torch.float64)
+    assert out["residual"].tolist() == [5.0, 1.0] and out["nnz_m"].tolist() == [1, 0]       # |2*3 - 1|, |0 - 1|
+    ls = ctx.reward_batch(torch.tensor([[1], [0]], dtype=torch.int64).cuda(), 0.5, "ls", torch.float64)
+    assert ls["residual"][0] == pytest.approx(0.0, abs=1e-12) and ls["residual"][1] == pytest.approx(1.0)
+    assert ctx.info().orig_residual_f64 == pytest.approx(8.0)                                 # |3*3 - 1|
+    ctx.close()
+    # E = 0: nothing to remove, M = 0, ||0 - I||_F = sqrt(n)
+    n = 7
+    empty = np.zeros(0, dtype=np.int64)
+    a = sp.identity(n, format="coo") * 2.0
+    ctx = SpaiContext(n, empty, empty, np.zeros(0), a.row, a.col, a.data)
+    for mode in ("copy", "ls"):
+        out = ctx.reward_batch(torch.tensor([[0, -1], [5, 3]], dtype=torch.int64).cuda(), 0.25, mode, torch.float64)
+        assert torch.allclose(out["residual"], torch.full((2,), float(np.sqrt(n)), dtype=torch.float64, device="cuda"))
+        assert out["nnz_m"].tolist() == [0, 0]
+    host = ctx.reward_batch(torch.tensor([[0, -1]], dtype=torch.int64), 0.25, "copy", torch.float32)
+    assert host["residual"][0] == pytest.approx(np.sqrt(n))
+    ctx.close()
+    # A with empty rows: candidates pointing at them gather nothing
+    rng = np.random.default_rng(3)
+    n = 30
+    a = sp.random(n, n, density=0.1, random_state=1, format="lil")
+    a[4, :] = 0
+    a[17, :] = 0
+    a = sp.csr_matrix(a)
+    a.eliminate_zeros()
+    r = np.repeat(np.arange(n), 4).astype(np.int64)
+    c = rng.integers(0, n, r.size).astype(np.int64)
+    c[:8] = [4, 17, 4, 17, 4, 4, 17, 17]
+    key = np.unique(r * n + c)
+    r, c = key // n, key % n
+    v = rng.uniform(-1, 1, r.size)
+    coo = a.tocoo()
+    ctx = SpaiContext(n, r, c, v, coo.row, coo.col, coo.data)
+    acts = synth.make_trajectories(r.size, 4, seed0=6)
+    want = orc.reward_batch_copy(n, r, c, v, a, acts, 0.5, dtype=np.float64)
+    got = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "copy", torch.float64)
+    np.testing.assert_allclose(got["residual"].cpu().numpy(), want["residual"], rtol=RTOL64, atol=ATOL64)
+    wls = orc.reward_batch_ls(n, r, c, a, acts, 0.5, dtype=np.float64, baseline_dtype=np.float64)
+    gls = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "ls", torch.float64)
+    np.testing.assert_allclose(gls["residual"].cpu().numpy(), wls["residual"], rtol=1e-9, atol=1e-9)
+    ctx.close()
