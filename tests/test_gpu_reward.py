@@ -385,7 +385,7 @@ def test_degenerate_shapes():
     out = ctx.reward_batch(torch.tensor([[1], [0]], dtype=torch.int64).cuda(), 0.5, "copy", torch.float64)
     assert out["residual"].tolist() == [5.0, 1.0] and out["nnz_m"].tolist() == [1, 0]       # |2*3 - 1|, |0 - 1|
     ls = ctx.reward_batch(torch.tensor([[1], [0]], dtype=torch.int64).cuda(), 0.5, "ls", torch.float64)
-    assert ls["residual"][0] == pytest.approx(0.0, abs=1e-12) and ls["residual"][1] == pytest.approx(1.0)
+    assert float(ls["residual"][0]) == pytest.approx(0.0, abs=1e-12) and float(ls["residual"][1]) == pytest.approx(1.0)
     assert ctx.info().orig_residual_f64 == pytest.approx(8.0)                                 # |3*3 - 1|
     ctx.close()
     # E = 0: nothing to remove, M = 0, ||0 - I||_F = sqrt(n)
@@ -398,7 +398,7 @@ def test_degenerate_shapes():
         assert torch.allclose(out["residual"], torch.full((2,), float(np.sqrt(n)), dtype=torch.float64, device="cuda"))
         assert out["nnz_m"].tolist() == [0, 0]
     host = ctx.reward_batch(torch.tensor([[0, -1]], dtype=torch.int64), 0.25, "copy", torch.float32)
-    assert host["residual"][0] == pytest.approx(np.sqrt(n))
+    assert float(host["residual"][0]) == pytest.approx(np.sqrt(n))
     ctx.close()
     # A with empty rows: candidates pointing at them gather nothing
     rng = np.random.default_rng(3)
