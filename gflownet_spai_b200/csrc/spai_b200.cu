@@ -397,7 +397,7 @@ static int k3_blocks_per_sm(int dtype, int nt) {
   int& c = cache[dtype == SPAI_F64][nt];
   if (c) return c;
   int v = 0;
-  const size_t smem = (size_t)K3_SMEM_BYTES;
+  const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>() : k3_smem_bytes<double>());
 #define SPAI_OCC(T, NT) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k3_copy_kernel<T, NT>, K3_THREADS, smem)
   if (dtype == SPAI_F32) {
     if (nt == 8) SPAI_OCC(float, 8); else if (nt == 4) SPAI_OCC(float, 4);
@@ -561,7 +561,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   int parts = s.parts;
   if (mode == SPAI_MODE_COPY) {
     const dim3 grid(s.gx, s.gy);
-    const size_t smem = (size_t)K3_SMEM_BYTES;
+    const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>() : k3_smem_bytes<double>());
     // tiles that intersect [row_lo, row_hi)
     const auto& tr = plan.tile_row_host;
     int t_lo = 0, t_n = plan.ntiles;
