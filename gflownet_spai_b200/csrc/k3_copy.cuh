@@ -28,14 +28,15 @@
 
 namespace spai {
 
-constexpr int K3_TILE_C = 880;       // records per staged tile
-constexpr int K3_TILE_R = 112;       // rows per staged tile (row headers)
+constexpr int K3_TILE_C = 1024;      // records per staged tile (16 KB)
+constexpr int K3_TILE_R = 128;       // rows per staged tile (2 KB of row headers)
 constexpr int K3_LIST = 128;         // per-warp compaction list (touching trajectories of a row)
 constexpr int K3_THREADS = 128;
 constexpr int K3_STAGE_BYTES = (K3_TILE_C + 1) * 16 + K3_TILE_R * 16;   // +1: prefetch slack
 constexpr int K3_WARPS = 4;
-template <typename T> constexpr int k3_smem_bytes() {
-  return 2 * K3_STAGE_BYTES + 64 + K3_WARPS * K3_LIST * (4 + (int)sizeof(T));
+// the compaction lists exist only in the COMPACT variant (6 vs 5 CTAs/SM for fp32)
+template <typename T> constexpr int k3_smem_bytes(bool compact) {
+  return 2 * K3_STAGE_BYTES + 64 + (compact ? K3_WARPS * K3_LIST * (4 + (int)sizeof(T)) : 0);
 }
 
 // ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: SYNCS / UBLKCP)
@@ -170,7 +171,7 @@ __device__ __forceinline__ T k3_row_single(const Rec* __restrict__ rp, int cnt, 
 // shared-memory list (ballot + popc) and evaluated 32 at a time, one trajectory
 // per lane; otherwise all 32*NT run (cfg5 with 1 % deletions: 66.7 -> 36.9 ms;
 // the dense headline workload pays ~3 % for the votes).
-template <typename T, int NT, typename Rec>
+template <typename T, int NT, bool COMPACT, typename Rec>
 __device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt, int sp, int k,
                                             bool first_diag, T base, MaskWindow<NT>& mw,
                                             const uint32_t* __restrict__ mp, int64_t Bp, int64_t W,
@@ -180,42 +181,52 @@ __device__ __forceinline__ void k3_row_fast(const Rec* __restrict__ rp, int cnt,
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
   uint32_t m[NT];
-  unsigned bal[NT];
-  int touching = 0;
+  uint32_t all = kmask;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     m[j] = __funnelshift_r(mw.lo[j], mw.hi[j], sh) & kmask;
-    bal[j] = __ballot_sync(0xffffffffu, m[j] != kmask);
-    touching += __popc(bal[j]);
+    all &= m[j];
   }
-  if (touching == 0) {
+  // one vote first: while every lane holds at least one touching trajectory (more than
+  // ~1/3 of them touch) the per-slot ballots below are never issued
+  const unsigned lanes_touch = __ballot_sync(0xffffffffu, all != kmask);
+  if (lanes_touch == 0) {
 #pragma unroll
     for (int j = 0; j < NT; ++j) rs[j] += base;
     return;
   }
-  if (touching <= (K3_LIST * 3) / 4 && touching <= 12 * NT) {
-    int at = 0;
+  if (COMPACT && lanes_touch != 0xffffffffu) {
+    unsigned bal[NT];
+    int touching = 0;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      if (m[j] != kmask) lm[at + __popc(bal[j] & lt)] = m[j]; else rs[j] += base;
-      at += __popc(bal[j]);
+      bal[j] = __ballot_sync(0xffffffffu, m[j] != kmask);
+      touching += __popc(bal[j]);
     }
-    __syncwarp();
-    for (int p0 = 0; p0 < touching; p0 += 32) {
-      const int idx = p0 + (threadIdx.x & 31);
-      const uint32_t mm = (idx < touching) ? lm[idx] : kmask;
-      const T v = k3_row_single<T, Rec>(rp, cnt, first_diag, mm);
-      if (idx < touching) lv[idx] = v;
-    }
-    __syncwarp();
-    at = 0;
+    if (touching <= (K3_LIST * 3) / 4 && touching <= 12 * NT) {
+      int at = 0;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      if (m[j] != kmask) rs[j] += lv[at + __popc(bal[j] & lt)];
-      at += __popc(bal[j]);
+      for (int j = 0; j < NT; ++j) {
+        if (m[j] != kmask) lm[at + __popc(bal[j] & lt)] = m[j]; else rs[j] += base;
+        at += __popc(bal[j]);
+      }
+      __syncwarp();
+      for (int p0 = 0; p0 < touching; p0 += 32) {
+        const int idx = p0 + (threadIdx.x & 31);
+        const uint32_t mm = (idx < touching) ? lm[idx] : kmask;
+        const T v = k3_row_single<T, Rec>(rp, cnt, first_diag, mm);
+        if (idx < touching) lv[idx] = v;
+      }
+      __syncwarp();
+      at = 0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (m[j] != kmask) rs[j] += lv[at + __popc(bal[j] & lt)];
+        at += __popc(bal[j]);
+      }
+      __syncwarp();
+      return;
     }
-    __syncwarp();
-    return;
   }
   T acc[NT];
   const T a0 = first_diag ? T(-1) : T(0);
@@ -269,7 +280,9 @@ __device__ __forceinline__ void k3_row_wide(const Rec* __restrict__ rp, int cnt,
   }
 }
 
-template <typename T, int NT>
+// COMPACT = false drops the compaction code (a few % faster when most trajectories touch
+// most rows: the host picks it from the trajectory length, see eval_masks).
+template <typename T, int NT, bool COMPACT>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* __restrict__ cptr,
                const RowHdr* __restrict__ rhdr, const T* __restrict__ row_base,
@@ -339,8 +352,8 @@ k3_copy_kernel(const typename RecOf<T>::type* __restrict__ recs, const int64_t* 
       const bool fd = h.flags & 1;
       if (h.k <= 32) {
         const T base = row_base[r0 + i];
-        if (staged) k3_row_fast<T, NT, Rec>(tile + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, lm, lv, rs);
-        else        k3_row_fast<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, lm, lv, rs);
+        if (staged) k3_row_fast<T, NT, COMPACT, Rec>(tile + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, lm, lv, rs);
+        else        k3_row_fast<T, NT, COMPACT, Rec>(recs + c0 + off, h.cnt, h.sp, h.k, fd, base, mw, mp, Bp, W, lm, lv, rs);
       } else {
         if (staged) k3_row_wide<T, NT, Rec>(tile + off, h.cnt, h.sp, fd, mp, Bp, rs);
         else        k3_row_wide<T, NT, Rec>(recs + c0 + off, h.cnt, h.sp, fd, mp, Bp, rs);

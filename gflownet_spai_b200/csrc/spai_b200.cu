@@ -392,13 +392,15 @@ struct EvalShape {       // launch geometry of one reward evaluation over Bc tra
 
 // resident CTAs per SM of the copy kernel instantiation (occupancy API, cached):
 // the grid is sized to ONE full wave so no half-empty second wave trails.
-static int k3_blocks_per_sm(int dtype, int nt) {
-  static int cache[2][9] = {};
-  int& c = cache[dtype == SPAI_F64][nt];
+static int k3_blocks_per_sm(int dtype, int nt, bool compact = false) {
+  static int cache[2][2][9] = {};
+  int& c = cache[compact][dtype == SPAI_F64][nt];
   if (c) return c;
   int v = 0;
-  const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>() : k3_smem_bytes<double>());
-#define SPAI_OCC(T, NT) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k3_copy_kernel<T, NT>, K3_THREADS, smem)
+  const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>(compact) : k3_smem_bytes<double>(compact));
+#define SPAI_OCC(T, NT)                                                                                          \
+  (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k3_copy_kernel<T, NT, true>, K3_THREADS, smem)    \
+           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k3_copy_kernel<T, NT, false>, K3_THREADS, smem))
   if (dtype == SPAI_F32) {
     if (nt == 8) SPAI_OCC(float, 8); else if (nt == 4) SPAI_OCC(float, 4);
     else if (nt == 2) SPAI_OCC(float, 2); else SPAI_OCC(float, 1);
@@ -517,7 +519,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
                       double res0, double flops0, double alpha, double* reward, double* residual,
                       int64_t* nnz_out, cudaStream_t st, PhaseTimer* pt, int* launches,
                       const long long* nnz_ready = nullptr, int64_t row_lo = 0, int64_t row_hi = -1,
-                      bool partial_only = false) {
+                      bool partial_only = false, int64_t t_hint = 0) {
   const int64_t W = P.words();
   if (row_hi < 0 || row_hi > plan.n) row_hi = plan.n;
   if (row_lo < 0) row_lo = 0;
@@ -560,8 +562,6 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   const unsigned int* fail_count_dev = nullptr;
   int parts = s.parts;
   if (mode == SPAI_MODE_COPY) {
-    const dim3 grid(s.gx, s.gy);
-    const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>() : k3_smem_bytes<double>());
     // tiles that intersect [row_lo, row_hi)
     const auto& tr = plan.tile_row_host;
     int t_lo = 0, t_n = plan.ntiles;
@@ -572,13 +572,30 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
       t_hi = std::max(t_lo, std::min(t_hi, plan.ntiles));
       t_n = (row_hi > row_lo) ? t_hi - t_lo : 0;
     }
+    // compaction pays when few of the 32*NT trajectories of a warp touch a given row: expected
+    // touching trajectories per (warp, row) ~ 32*NT * deletions/n (hint = longest trajectory; 0 = unknown)
+    bool compact = t_hint <= 0 || (double)t_hint * 32.0 * s.nt <= 128.0 * (double)plan.n;
+    if (const char* v = getenv("SPAI_K3_COMPACT")) compact = atoi(v) != 0;      // A/B switch
+    const size_t smem = (size_t)(dtype == SPAI_F32 ? k3_smem_bytes<float>(compact) : k3_smem_bytes<double>(compact));
+    // the workspace holds s.gx partial rows (sized for the smaller-footprint variant); the
+    // compact variant keeps fewer CTAs resident, so its one-wave grid is narrower
+    int gx = s.gx;
+    if (compact) gx = std::max(1, std::min(gx, sm_count * k3_blocks_per_sm(dtype, s.nt, true) / s.gy));
+    parts = gx;
+    const dim3 grid(gx, s.gy);
 #define SPAI_K3(T, NT)                                                                          \
-  k3_copy_kernel<T, NT><<<grid, K3_THREADS, smem, st>>>(                                        \
-      reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy), plan.cptr, plan.rhdr,    \
-      reinterpret_cast<const T*>(plan.row_base), plan.tile_row + t_lo, t_n, maskT, Bp, W, partial,  \
-      (int)row_lo, (int)row_hi)
+  do {                                                                                          \
+    const typename RecOf<T>::type* rc_ = reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_copy); \
+    const T* rb_ = reinterpret_cast<const T*>(plan.row_base);                                   \
+    if (compact)                                                                                \
+      k3_copy_kernel<T, NT, true><<<grid, K3_THREADS, smem, st>>>(rc_, plan.cptr, plan.rhdr, rb_, \
+          plan.tile_row + t_lo, t_n, maskT, Bp, W, partial, (int)row_lo, (int)row_hi);          \
+    else                                                                                        \
+      k3_copy_kernel<T, NT, false><<<grid, K3_THREADS, smem, st>>>(rc_, plan.cptr, plan.rhdr, rb_, \
+          plan.tile_row + t_lo, t_n, maskT, Bp, W, partial, (int)row_lo, (int)row_hi);          \
+  } while (0)
     if (t_n == 0) {
-      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)s.parts * Bp * 8, st));
+      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); parts = 1;
     } else if (dtype == SPAI_F32) {
       if (s.nt == 8) SPAI_K3(float, 8); else if (s.nt == 4) SPAI_K3(float, 4);
       else if (s.nt == 2) SPAI_K3(float, 2); else SPAI_K3(float, 1);
@@ -1089,7 +1106,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
     SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
                         (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready, c->row_lo,
-                        c->row_hi, c->partial_only));
+                        c->row_hi, c->partial_only, src == FROM_TAKEN_DEV ? 0 : T));
     if (pt->on) cudaEventRecord(pt->ev[4], st);
     if (out_host) {
       if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
