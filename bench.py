@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the grid (testing only)")
-    ap.add_argument("--mode", default="copy", choices=["copy", "ls"])
+    ap.add_argument("--mode", default="copy", choices=["copy", "ls", "ls_gram"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (0 = config default)")
     ap.add_argument("--cpu-sample", type=int, default=96, help="trajectories in the CPU-baseline sample")
@@ -272,6 +272,9 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+KNAMES = {"copy": "k3_copy_kernel", "ls": "k2_ls_kernel", "ls_gram": "k2g_solve_kernel"}
+
+
 def algorithmic_bytes(ctx, p, acts_dev, mode, wbytes):
     """SURVEY.md §8d gather-inclusive G summed over the batch, from the inputs
     alone: for every kept candidate (i, c): 4 (pattern col id) + w (M value, copy
@@ -384,7 +387,7 @@ def run_b200_arm(args):
     kern = {
         "k0_masks(actions->kept bitmask)": {"ms": ph["masks"], "algorithmic_bytes": k0_bytes},
         "k0_transpose+popcount": {"ms": ph["transpose"], "algorithmic_bytes": 3.0 * B * W * 4},
-        ("k3_copy_kernel" if args.mode == "copy" else "k2_ls_kernel"): {"ms": ph["reward"], "algorithmic_bytes": g_bytes},
+        KNAMES[args.mode]: {"ms": ph["reward"], "algorithmic_bytes": g_bytes},
         "k3_finalize": {"ms": ph["finalize"], "algorithmic_bytes": 16.0 * B},
     }
     for v in kern.values():
@@ -392,7 +395,7 @@ def run_b200_arm(args):
         v["share"] = v["ms"] / max(sum(ph.values()), 1e-9)
     info0 = ctx.info()
     rec_bytes = 16.0 * info0.contributions + 16.0 * p.n
-    kname = "k3_copy_kernel" if args.mode == "copy" else "k2_ls_kernel"
+    kname = KNAMES[args.mode]
     kern[kname]["compulsory_bytes"] = float(B) * W * 4 + rec_bytes + 8.0 * B      # masks once + plan once + sums
     kern[kname]["compulsory_gbps"] = kern[kname]["compulsory_bytes"] / max(kern[kname]["ms"], 1e-9) / 1e6
     dom = max(kern, key=lambda k: kern[k]["ms"])
@@ -451,8 +454,11 @@ def run_b200_arm(args):
     # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
     extras = {}
     if rank == 0 and not args.no_extras and args.mode == "copy":
-        sub = acts[: min(B, 1024 if args.config in ("cfg1", "cfg2") else 64)]
-        for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("copy", torch.float64)):
+        for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("ls_gram", torch.float32),
+                       ("ls_gram", torch.float64), ("copy", torch.float64)):
+            # the Householder kernels get a smaller batch (they are ~10x slower); Gram mode runs the whole batch
+            small = 1024 if args.config in ("cfg1", "cfg2") else 64
+            sub = acts[: min(B, small)] if md == "ls" or args.config not in ("cfg1", "cfg2") else acts
             try:
                 for _ in range(2):
                     ctx.reward_batch(sub, 0.5, md, dt)
@@ -477,7 +483,7 @@ def run_b200_arm(args):
             g.manual_seed(7)
             short = torch.randint(0, p.num_edges, (B, 65), generator=g, device=dev, dtype=torch.int64)
             short[:, -1] = p.num_edges
-            for md in ("copy", "ls"):
+            for md in ("copy", "ls", "ls_gram"):
                 for _ in range(2):
                     ctx.reward_batch(short, 0.5, md, tdtype)
                 torch.cuda.synchronize()
@@ -506,6 +512,12 @@ def run_b200_arm(args):
                                          sel, 0.5, dtype=npdt)["reward"]
             got = ctx.reward_batch(acts[:2], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
             parity = {"trajectories": 2, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
+        elif p.n <= 70000:
+            npdt = np.float32 if args.dtype == "f32" else np.float64
+            want = orc.reward_batch_ls(p.n, p.edge_row, p.edge_col, p.a, sel[:1], 0.5, dtype=npdt,
+                                       baseline_dtype=npdt)["reward"]
+            got = ctx.reward_batch(acts[:1], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
+            parity = {"trajectories": 1, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
         # ls-mode CPU restatement (LAPACK lstsq per row), bounded sample: 2048 rows of one pattern
         try:
             import scipy.sparse as _sp

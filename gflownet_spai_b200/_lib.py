@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libspai_b200.so")
 SPAI_OK, SPAI_ERR_INVALID, SPAI_ERR_CUDA, SPAI_ERR_UNSUPPORTED, SPAI_ERR_NOMEM = range(5)
 MODE_COPY, MODE_LS = 0, 1
 F32, F64 = 0, 1
-MODES = {"copy": MODE_COPY, "ls": MODE_LS}
+MODE_LS_GRAM = 2
+MODES = {"copy": MODE_COPY, "ls": MODE_LS, "ls_gram": MODE_LS_GRAM}
 
 EXPORTS = [
     "spai_abi_version", "spai_last_error", "spai_device_count", "spai_ctx_create",

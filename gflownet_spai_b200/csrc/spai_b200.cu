@@ -12,6 +12,7 @@
 #include "k0_masks.cuh"
 #include "k1_plan.cuh"
 #include "k2_ls.cuh"
+#include "k2g_gram.cuh"
 #include "k3_copy.cuh"
 #include "k4_sample.cuh"
 #include "spai_internal.cuh"
@@ -385,6 +386,7 @@ struct EvalShape {       // launch geometry of one reward evaluation over Bc tra
   int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
   int nt = 1, gx = 1, gy = 1;                       // copy kernel
   int ls_gx[LS_NCLASS] = {}, ls_gy[LS_NCLASS] = {}, ls_ntg[LS_NCLASS] = {};
+  int gram_gx[2] = {}, gram_gy = 1;                 // semi-normal-equation classes (ls_gram mode)
   int parts = 1;
   int64_t generic_work = 0, generic_cmap = 0, generic_warps = 0;
   bool has_column_class = false;      // column-per-lane kernels may hand tiles to the generic kernel
@@ -413,6 +415,17 @@ static int k3_blocks_per_sm(int dtype, int nt, bool compact = false) {
   return c;
 }
 
+// row list of QR class c: in ls_gram mode only the rows no Gram class takes
+static inline int64_t ls_count(const Plan& p, int mode, int c) {
+  return mode == SPAI_MODE_LS_GRAM ? p.rest_count[c] : p.class_count[c];
+}
+static inline const int32_t* ls_rows(const Plan& p, int mode, int c) {
+  return mode == SPAI_MODE_LS_GRAM ? p.rest_rows[c] : p.class_rows[c];
+}
+static inline const std::vector<int32_t>& ls_rows_host(const Plan& p, int mode, int c) {
+  return mode == SPAI_MODE_LS_GRAM ? p.rest_rows_host[c] : p.class_rows_host[c];
+}
+
 static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, int sm_count) {
   EvalShape s;
   if (mode == SPAI_MODE_COPY) {
@@ -428,18 +441,29 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     s.Bp = round_up(Bc, 32);
     const int64_t Bp = s.Bp;
     s.parts = 0;
+    if (mode == SPAI_MODE_LS_GRAM) {
+      s.gram_gy = (int)ceil_div(Bp, (int64_t)K3_THREADS);
+      for (int g = 0; g < 2; ++g) {
+        if (!plan.gram_count[g]) continue;
+        s.has_column_class = true;                   // ill-conditioned tiles go to the generic kernel
+        const int target = sm_count * (g == 0 ? 4 : 2);
+        s.gram_gx[g] = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(plan.gram_count[g], 16),
+                                                                   std::max(1, target / s.gram_gy)));
+        s.parts += s.gram_gx[g];
+      }
+    }
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
-      if (!plan.class_count[c]) continue;
+      if (!ls_count(plan, mode, c)) continue;
       const LsClass& L = kLsClasses[c];
       const int groups = K2_NW * (32 / ls_class_lanes(L));
       s.has_column_class = true;      // every register kernel assumes full rank and may hand tiles over
       s.ls_ntg[c] = (int)std::min<int64_t>(K2_MAX_NTG, ceil_div(Bp, groups));
       s.ls_gy[c] = (int)ceil_div(Bp, (int64_t)groups * s.ls_ntg[c]);
       const int target = sm_count * 12;
-      s.ls_gx[c] = (int)std::max<int64_t>(1, std::min<int64_t>(plan.class_count[c], std::max(1, target / s.ls_gy[c])));
+      s.ls_gx[c] = (int)std::max<int64_t>(1, std::min<int64_t>(ls_count(plan, mode, c), std::max(1, target / s.ls_gy[c])));
       s.parts += s.ls_gx[c];
     }
-    if (plan.class_count[LS_GENERIC] || s.has_column_class) {
+    if (ls_count(plan, mode, LS_GENERIC) || s.has_column_class) {
       s.generic_warps = (int64_t)sm_count * 16;
       const int64_t gq = s.has_column_class ? plan.max_q : plan.generic_max_q;
       const int64_t gk = s.has_column_class ? plan.max_k : plan.generic_max_k;
@@ -467,7 +491,7 @@ static int64_t eval_bytes(const Plan& plan, const EvalShape& s, int64_t W, int d
 }
 
 template <typename T>
-static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const EvalShape& s,
+static int launch_ls_class(int c, const int32_t* crows, const Plan& plan, const Pattern& P, const EvalShape& s,
                            const uint32_t* maskT, int64_t Bp, int64_t Bc, double* partial, int2* fail_pairs,
                            unsigned int* fail_count, cudaStream_t st, int64_t roff, int64_t rcnt) {
   using Rec = typename RecOf<T>::type;
@@ -477,13 +501,13 @@ static int launch_ls_class(int c, const Plan& plan, const Pattern& P, const Eval
 #define SPAI_LS_ROW(IDX, KMAX, G, QL)                                                          \
   case IDX:                                                                                    \
     k2_ls_kernel<T, KMAX, G, QL><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,  \
-        plan.class_rows[c] + roff, rcnt, maskT, Bp, s.ls_ntg[c], partial,                       \
+        crows + roff, rcnt, maskT, Bp, s.ls_ntg[c], partial,                                    \
         plan.row_base_ls, Bc, fail_pairs, fail_count, LS_FAIL_CAP);                            \
     break;
 #define SPAI_LS_COL(IDX, W, QMAX)                                                              \
   case IDX:                                                                                    \
     k2c_ls_kernel<T, W, QMAX><<<grid, block, 0, st>>>(recs, plan.cptr, P.sptr, plan.r_diag,     \
-        plan.class_rows[c] + roff, rcnt, maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs,       \
+        crows + roff, rcnt, maskT, Bp, Bc, s.ls_ntg[c], partial, fail_pairs,                    \
         fail_count, LS_FAIL_CAP, plan.row_base_ls);                                            \
     break;
   switch (c) {
@@ -526,7 +550,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   if (row_lo > row_hi) row_lo = row_hi;
   // sub-range of a sorted class row list
   auto sub = [&](int c, int64_t* off, int64_t* cnt) {
-    const auto& v = plan.class_rows_host[c];
+    const auto& v = c >= 100 ? plan.gram_rows_host[c - 100] : ls_rows_host(plan, mode, c);
     const int64_t a = std::lower_bound(v.begin(), v.end(), (int32_t)row_lo) - v.begin();
     const int64_t b = std::lower_bound(v.begin(), v.end(), (int32_t)std::min<int64_t>(row_hi, INT32_MAX)) - v.begin();
     *off = a; *cnt = b - a;
@@ -622,15 +646,34 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     }
     int off = 0;
     bool any = false;
+    if (mode == SPAI_MODE_LS_GRAM) {
+      if (!plan.gram_ready) { set_error("plan was built without Gram records"); return SPAI_ERR_INVALID; }
+      for (int g = 0; g < 2; ++g) {
+        if (!plan.gram_count[g]) continue;
+        double* pp = partial + (int64_t)off * Bp;
+        int64_t roff, rcnt;
+        sub(100 + g, &roff, &rcnt);
+        const dim3 grid(s.gram_gx[g], s.gram_gy);
+#define SPAI_GRAM(T, K)                                                                          \
+  k2g_solve_kernel<T, K><<<grid, K3_THREADS, GramGeom<T, K>::SMEM, st>>>(                          \
+      plan.gram[g] + roff * GramGeom<T, K>::RB, rcnt, maskT, Bp, W, Bc, pp, fail_pairs, fail_count, LS_FAIL_CAP)
+        if (dtype == SPAI_F32) { if (g == 0) SPAI_GRAM(float, 8); else SPAI_GRAM(float, 16); }
+        else SPAI_GRAM(double, 8);
+#undef SPAI_GRAM
+        SPAI_CUDA(cudaGetLastError());
+        off += s.gram_gx[g]; ++nl; any = true;
+      }
+    }
     for (int c = 0; c < LS_NCLASS - 1; ++c) {
-      if (!plan.class_count[c]) continue;
+      if (!ls_count(plan, mode, c)) continue;
       double* pp = partial + (int64_t)off * Bp;
       int64_t roff, rcnt;
       sub(c, &roff, &rcnt);
+      const int32_t* crows = ls_rows(plan, mode, c);
       if (dtype == SPAI_F32)
-        SPAI_TRY(launch_ls_class<float>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
+        SPAI_TRY(launch_ls_class<float>(c, crows, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
       else
-        SPAI_TRY(launch_ls_class<double>(c, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
+        SPAI_TRY(launch_ls_class<double>(c, crows, plan, P, s, maskT, Bp, Bc, pp, fail_pairs, fail_count, st, roff, rcnt));
       off += s.ls_gx[c]; ++nl; any = true;
     }
     if (!any) { SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); parts = 1; }
@@ -639,12 +682,12 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
       const unsigned blocks = (unsigned)(s.generic_warps / 4);
       for (int pass = 0; pass < 2; ++pass) {
         // pass 0: the rows classified as generic; pass 1: tiles handed over by the column kernels
-        if (pass == 0 && !plan.class_count[LS_GENERIC]) continue;
+        if (pass == 0 && !ls_count(plan, mode, LS_GENERIC)) continue;
         if (pass == 1 && !s.has_column_class) continue;
         const int2* pairs = pass ? fail_pairs : nullptr;
-        int64_t goff = 0, gcnt = plan.class_count[LS_GENERIC];
+        int64_t goff = 0, gcnt = ls_count(plan, mode, LS_GENERIC);
         if (!pass) sub(LS_GENERIC, &goff, &gcnt);
-        const int32_t* grows = plan.class_rows[LS_GENERIC] ? plan.class_rows[LS_GENERIC] + goff : nullptr;
+        const int32_t* grows = ls_rows(plan, mode, LS_GENERIC) ? ls_rows(plan, mode, LS_GENERIC) + goff : nullptr;
         if (dtype == SPAI_F32)
           k2_ls_generic_kernel<float><<<blocks, 128, 0, st>>>(
               reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, P.sptr, plan.r_q, plan.r_diag,
@@ -712,6 +755,59 @@ static int ensure_plan(spai_ctx* c, int dtype, bool want_ls, cudaStream_t st) {
                       c->plan[dtype], st));
   c->plan_ready[dtype] = true;
   c->plan_has_ls[dtype] = want_ls || dtype == SPAI_F32;
+  return SPAI_OK;
+}
+
+// ls_gram mode: split the rows with a non-empty union into the Gram classes and the rest
+// (which keep their QR class), then form every Gram row once (k2g_build_kernel).
+static int ensure_gram(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.gram_ready) return SPAI_OK;
+  if (!plan.rec_ls || !plan.row_base_ls) { set_error("ls_gram: plan has no ls records"); return SPAI_ERR_INVALID; }
+  Arena& ar = c->plan_arena[dtype];
+  const HostPattern& hp = c->hp;
+  std::vector<char> row_dup(plan.n, 0);
+  for (size_t g = 0; g < hp.dup_start.size(); ++g) {
+    const int32_t s0 = hp.dup_start[g];
+    row_dup[std::upper_bound(hp.sptr.begin(), hp.sptr.end(), s0) - hp.sptr.begin() - 1] = 1;
+  }
+  const int klimit = (dtype == SPAI_F32) ? 16 : 8;
+  std::vector<int32_t> gr[2];
+  for (int cl = 0; cl < LS_NCLASS; ++cl) {
+    plan.rest_rows_host[cl].clear();
+    for (int32_t i : plan.class_rows_host[cl]) {
+      const int k = hp.sptr[i + 1] - hp.sptr[i];
+      if (!row_dup[i] && k <= klimit) gr[k <= 8 ? 0 : 1].push_back(i);
+      else plan.rest_rows_host[cl].push_back(i);
+    }
+    plan.rest_count[cl] = (int64_t)plan.rest_rows_host[cl].size();
+    plan.rest_rows[cl] = nullptr;
+    if (plan.rest_count[cl]) SPAI_TRY(ar.upload(&plan.rest_rows[cl], plan.rest_rows_host[cl]));
+  }
+  for (int g = 0; g < 2; ++g) {
+    std::sort(gr[g].begin(), gr[g].end());
+    plan.gram_rows_host[g] = gr[g];
+    plan.gram_count[g] = (int64_t)gr[g].size();
+    plan.gram[g] = nullptr;
+    if (gr[g].empty()) continue;
+    const int64_t rb = (dtype == SPAI_F32) ? (g == 0 ? GramGeom<float, 8>::RB : GramGeom<float, 16>::RB)
+                                           : GramGeom<double, 8>::RB;
+    SPAI_TRY(ar.alloc(&plan.gram[g], plan.gram_count[g] * rb));
+    Arena tmp;
+    int32_t* rows_dev = nullptr;
+    SPAI_TRY(tmp.upload(&rows_dev, gr[g]));
+    const unsigned blocks = (unsigned)ceil_div(plan.gram_count[g], 4);
+#define SPAI_GB(T, K)                                                                                   \
+  k2g_build_kernel<T, K><<<blocks, 128, 0, st>>>(reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_ls), \
+      plan.cptr, c->P.sptr, plan.r_diag, plan.row_base_ls, rows_dev, plan.gram_count[g], plan.gram[g])
+    if (dtype == SPAI_F32) { if (g == 0) SPAI_GB(float, 8); else SPAI_GB(float, 16); }
+    else SPAI_GB(double, 8);
+#undef SPAI_GB
+    SPAI_CUDA(cudaGetLastError());
+    SPAI_CUDA(cudaStreamSynchronize(st));          // rows_dev is released on scope exit
+  }
+  plan.bytes = ar.bytes;
+  plan.gram_ready = true;
   return SPAI_OK;
 }
 
@@ -963,7 +1059,7 @@ enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
 static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t B, int64_t T, int64_t ld,
                          double alpha, int mode, int dtype, double* reward, double* residual,
                          int64_t* nnz_m, bool out_host, uint8_t* kept_bytes_dev, void* stream) {
-  if (!c || B < 0 || (B && !input && (src == FROM_TAKEN_DEV || T > 0)) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS) ||
+  if (!c || B < 0 || (B && !input && (src == FROM_TAKEN_DEV || T > 0)) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS && mode != SPAI_MODE_LS_GRAM) ||
       (dtype != SPAI_F32 && dtype != SPAI_F64) || (src != FROM_TAKEN_DEV && (T < 0 || ld < T))) {
     set_error("reward: invalid arguments");
     return SPAI_ERR_INVALID;
@@ -972,7 +1068,8 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   DeviceGuard guard(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool mask_only = kept_bytes_dev != nullptr;
-  if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode == SPAI_MODE_LS, st));
+  if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode != SPAI_MODE_COPY, st));
+  if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
   const Plan& plan = c->plan[mask_only ? SPAI_F32 : dtype];
   const Pattern& P = c->P;
   const int64_t W = P.words();

@@ -134,6 +134,15 @@ struct Plan {
   std::vector<int32_t> class_rows_host[LS_NCLASS];   // sorted ascending (row-range evaluation)
   std::vector<int64_t> missing_prefix;               // [n+1] prefix count of rows without a diagonal slot
   int64_t generic_max_q = 0, generic_max_k = 0;
+  // ls_gram mode (built on first use): rows solved through the semi-normal equations
+  // (gram class 0: k <= 8; class 1: 8 < k <= 16, fp32 only); every other row keeps its QR class
+  bool gram_ready = false;
+  unsigned char* gram[2] = {};                       // [gram_count][GramGeom::RB]
+  int64_t gram_count[2] = {};
+  std::vector<int32_t> gram_rows_host[2];            // sorted ascending
+  int32_t* rest_rows[LS_NCLASS] = {};
+  int64_t rest_count[LS_NCLASS] = {};
+  std::vector<int32_t> rest_rows_host[LS_NCLASS];
   double g_bytes_full = 0;        // SURVEY §8d G with every candidate kept (bytes / pattern)
   int64_t bytes = 0;
 };

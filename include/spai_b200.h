@@ -39,8 +39,14 @@ enum spai_status {
 enum spai_mode {
   SPAI_MODE_COPY = 0, /* surviving entries keep their values: what the reference
                          computes (gflownet/utils.py:331-337)                  */
-  SPAI_MODE_LS = 1    /* re-solve every row's least-squares problem on its
-                         pattern (BASELINE.json north star; no reference code) */
+  SPAI_MODE_LS = 1,   /* re-solve every row's least-squares problem on its
+                         pattern (BASELINE.json north star; no reference code):
+                         Householder QR on the gathered tile                    */
+  SPAI_MODE_LS_GRAM = 2 /* the same least-squares residual through the semi-normal
+                         equations: the row's Gram matrix is formed once per
+                         context, a (row, pattern) solve is a masked k x k LDL^T
+                         (rows with <= 8 candidates, <= 16 in fp32); other rows
+                         and ill-conditioned tiles go to the Householder kernels */
 };
 
 enum spai_dtype { SPAI_F32 = 0, SPAI_F64 = 1 };
