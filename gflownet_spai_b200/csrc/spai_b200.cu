@@ -386,7 +386,7 @@ struct EvalShape {       // launch geometry of one reward evaluation over Bc tra
   int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
   int nt = 1, gx = 1, gy = 1;                       // copy kernel
   int ls_gx[LS_NCLASS] = {}, ls_gy[LS_NCLASS] = {}, ls_ntg[LS_NCLASS] = {};
-  int gram_gx[2] = {}, gram_gy = 1;                 // semi-normal-equation classes (ls_gram mode)
+  int gram_gx[GRAM_NCLASS] = {}, gram_gy[GRAM_NCLASS] = {};   // semi-normal-equation classes (ls_gram mode)
   int parts = 1;
   int64_t generic_work = 0, generic_cmap = 0, generic_warps = 0;
   bool has_column_class = false;      // column-per-lane kernels may hand tiles to the generic kernel
@@ -413,6 +413,22 @@ static int k3_blocks_per_sm(int dtype, int nt, bool compact = false) {
   if (cudaGetLastError() != cudaSuccess || v <= 0) v = 4;
   c = v;
   return c;
+}
+
+// Gram classes (ls_gram mode): which kernel solves rows with k <= kmax in which precision.
+//   lanes = 1: k2g_solve_kernel<T,K> (packed triangle); lanes > 1: k2gd_solve_kernel<T,K,G> (full matrix)
+struct GramVariant { int kmax, lanes; int64_t rb; int smem; };
+static GramVariant gram_variant(int dtype, int g) {
+  if (dtype == SPAI_F32) {
+    if (g == 0) return {8, 1, GramGeom<float, 8, false>::RB, GramGeom<float, 8, false>::STAGES};
+    if (g == 1) return {16, 1, GramGeom<float, 16, false>::RB, GramGeom<float, 16, false>::STAGES};
+    return {32, 4, GramGeom<float, 32, true>::RB, GramDist<float, 32, 4>::SMEM};
+  }
+  if (g == 0) return {8, 1, GramGeom<double, 8, false>::RB, GramGeom<double, 8, false>::STAGES};
+  // lanes per problem: measured on B200 (B = 256): k <= 16 fp64 2 lanes 13.7 ms vs 4 lanes 17.5 ms (cfg3);
+  // k <= 32 fp64 8 lanes 106 ms vs 16 lanes 152 ms, fp32 4 lanes 52.7 ms vs 8 lanes 56.1 ms (cfg4)
+  if (g == 1) return {16, 2, GramGeom<double, 16, true>::RB, GramDist<double, 16, 2>::SMEM};
+  return {32, 8, GramGeom<double, 32, true>::RB, GramDist<double, 32, 8>::SMEM};
 }
 
 // row list of QR class c: in ls_gram mode only the rows no Gram class takes
@@ -442,13 +458,14 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     const int64_t Bp = s.Bp;
     s.parts = 0;
     if (mode == SPAI_MODE_LS_GRAM) {
-      s.gram_gy = (int)ceil_div(Bp, (int64_t)K3_THREADS);
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < GRAM_NCLASS; ++g) {
         if (!plan.gram_count[g]) continue;
+        const GramVariant v = gram_variant(dtype, g);
         s.has_column_class = true;                   // ill-conditioned tiles go to the generic kernel
-        const int target = sm_count * (g == 0 ? 4 : 2);
+        s.gram_gy[g] = (int)ceil_div(Bp, (int64_t)(K3_THREADS / v.lanes));
+        const int target = sm_count * (g == 0 ? 4 : 2) * 4;
         s.gram_gx[g] = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(plan.gram_count[g], 16),
-                                                                   std::max(1, target / s.gram_gy)));
+                                                                   std::max(1, target / s.gram_gy[g])));
         s.parts += s.gram_gx[g];
       }
     }
@@ -648,18 +665,26 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     bool any = false;
     if (mode == SPAI_MODE_LS_GRAM) {
       if (!plan.gram_ready) { set_error("plan was built without Gram records"); return SPAI_ERR_INVALID; }
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < GRAM_NCLASS; ++g) {
         if (!plan.gram_count[g]) continue;
         double* pp = partial + (int64_t)off * Bp;
         int64_t roff, rcnt;
         sub(100 + g, &roff, &rcnt);
-        const dim3 grid(s.gram_gx[g], s.gram_gy);
+        const dim3 grid(s.gram_gx[g], s.gram_gy[g]);
+        const GramVariant gv = gram_variant(dtype, g);
+        const unsigned char* gp = plan.gram[g] + roff * gv.rb;
 #define SPAI_GRAM(T, K)                                                                          \
-  k2g_solve_kernel<T, K><<<grid, K3_THREADS, GramGeom<T, K>::SMEM, st>>>(                          \
-      plan.gram[g] + roff * GramGeom<T, K>::RB, rcnt, maskT, Bp, W, Bc, pp, fail_pairs, fail_count, LS_FAIL_CAP)
-        if (dtype == SPAI_F32) { if (g == 0) SPAI_GRAM(float, 8); else SPAI_GRAM(float, 16); }
-        else SPAI_GRAM(double, 8);
+  k2g_solve_kernel<T, K><<<grid, K3_THREADS, gv.smem, st>>>(gp, rcnt, maskT, Bp, W, Bc, pp, fail_pairs, fail_count, LS_FAIL_CAP)
+#define SPAI_GRAMD(T, K, G)                                                                      \
+  k2gd_solve_kernel<T, K, G><<<grid, K3_THREADS, gv.smem, st>>>(gp, rcnt, maskT, Bp, W, Bc, pp, fail_pairs, fail_count, LS_FAIL_CAP)
+        if (dtype == SPAI_F32) {
+          if (g == 0) SPAI_GRAM(float, 8); else if (g == 1) SPAI_GRAM(float, 16);
+          else SPAI_GRAMD(float, 32, 4);
+        } else if (g == 0) SPAI_GRAM(double, 8);
+        else if (g == 1) SPAI_GRAMD(double, 16, 2);
+        else SPAI_GRAMD(double, 32, 8);
 #undef SPAI_GRAM
+#undef SPAI_GRAMD
         SPAI_CUDA(cudaGetLastError());
         off += s.gram_gx[g]; ++nl; any = true;
       }
@@ -771,37 +796,38 @@ static int ensure_gram(spai_ctx* c, int dtype, cudaStream_t st) {
     const int32_t s0 = hp.dup_start[g];
     row_dup[std::upper_bound(hp.sptr.begin(), hp.sptr.end(), s0) - hp.sptr.begin() - 1] = 1;
   }
-  const int klimit = (dtype == SPAI_F32) ? 16 : 8;
-  std::vector<int32_t> gr[2];
+  const int klimit = 32;
+  std::vector<int32_t> gr[GRAM_NCLASS];
   for (int cl = 0; cl < LS_NCLASS; ++cl) {
     plan.rest_rows_host[cl].clear();
     for (int32_t i : plan.class_rows_host[cl]) {
       const int k = hp.sptr[i + 1] - hp.sptr[i];
-      if (!row_dup[i] && k <= klimit) gr[k <= 8 ? 0 : 1].push_back(i);
+      if (!row_dup[i] && k <= klimit) gr[k <= 8 ? 0 : (k <= 16 ? 1 : 2)].push_back(i);
       else plan.rest_rows_host[cl].push_back(i);
     }
     plan.rest_count[cl] = (int64_t)plan.rest_rows_host[cl].size();
     plan.rest_rows[cl] = nullptr;
     if (plan.rest_count[cl]) SPAI_TRY(ar.upload(&plan.rest_rows[cl], plan.rest_rows_host[cl]));
   }
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < GRAM_NCLASS; ++g) {
     std::sort(gr[g].begin(), gr[g].end());
     plan.gram_rows_host[g] = gr[g];
     plan.gram_count[g] = (int64_t)gr[g].size();
     plan.gram[g] = nullptr;
     if (gr[g].empty()) continue;
-    const int64_t rb = (dtype == SPAI_F32) ? (g == 0 ? GramGeom<float, 8>::RB : GramGeom<float, 16>::RB)
-                                           : GramGeom<double, 8>::RB;
-    SPAI_TRY(ar.alloc(&plan.gram[g], plan.gram_count[g] * rb));
+    SPAI_TRY(ar.alloc(&plan.gram[g], plan.gram_count[g] * gram_variant(dtype, g).rb));
     Arena tmp;
     int32_t* rows_dev = nullptr;
     SPAI_TRY(tmp.upload(&rows_dev, gr[g]));
     const unsigned blocks = (unsigned)ceil_div(plan.gram_count[g], 4);
-#define SPAI_GB(T, K)                                                                                   \
-  k2g_build_kernel<T, K><<<blocks, 128, 0, st>>>(reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_ls), \
+#define SPAI_GB(T, K, FULL)                                                                             \
+  k2g_build_kernel<T, K, FULL><<<blocks, 128, 0, st>>>(reinterpret_cast<const typename RecOf<T>::type*>(plan.rec_ls), \
       plan.cptr, c->P.sptr, plan.r_diag, plan.row_base_ls, rows_dev, plan.gram_count[g], plan.gram[g])
-    if (dtype == SPAI_F32) { if (g == 0) SPAI_GB(float, 8); else SPAI_GB(float, 16); }
-    else SPAI_GB(double, 8);
+    if (dtype == SPAI_F32) {
+      if (g == 0) SPAI_GB(float, 8, false); else if (g == 1) SPAI_GB(float, 16, false); else SPAI_GB(float, 32, true);
+    } else if (g == 0) SPAI_GB(double, 8, false);
+    else if (g == 1) SPAI_GB(double, 16, true);
+    else SPAI_GB(double, 32, true);
 #undef SPAI_GB
     SPAI_CUDA(cudaGetLastError());
     SPAI_CUDA(cudaStreamSynchronize(st));          // rows_dev is released on scope exit

@@ -106,6 +106,7 @@ struct CsrA {               // original matrix, coalesced
 
 constexpr int LS_NCLASS = 8;     // last class = generic fallback
 constexpr int LS_GENERIC = LS_NCLASS - 1;
+constexpr int GRAM_NCLASS = 3;
 
 struct Plan {
   int dtype = -1;
@@ -135,11 +136,12 @@ struct Plan {
   std::vector<int64_t> missing_prefix;               // [n+1] prefix count of rows without a diagonal slot
   int64_t generic_max_q = 0, generic_max_k = 0;
   // ls_gram mode (built on first use): rows solved through the semi-normal equations
-  // (gram class 0: k <= 8; class 1: 8 < k <= 16, fp32 only); every other row keeps its QR class
+  // (gram class 0: k <= 8; 1: 8 < k <= 16; 2: 16 < k <= 32, fp64 only); every other row keeps
+  // its QR class
   bool gram_ready = false;
-  unsigned char* gram[2] = {};                       // [gram_count][GramGeom::RB]
-  int64_t gram_count[2] = {};
-  std::vector<int32_t> gram_rows_host[2];            // sorted ascending
+  unsigned char* gram[GRAM_NCLASS] = {};             // [gram_count][GramGeom::RB]
+  int64_t gram_count[GRAM_NCLASS] = {};
+  std::vector<int32_t> gram_rows_host[GRAM_NCLASS];  // sorted ascending
   int32_t* rest_rows[LS_NCLASS] = {};
   int64_t rest_count[LS_NCLASS] = {};
   std::vector<int32_t> rest_rows_host[LS_NCLASS];

@@ -270,7 +270,8 @@ class PreconditionerEnv(Env):
 
     Extra keyword arguments (not in the reference): ``device`` (CUDA index),
     ``mode`` ("copy" = the reference's semantics, "ls" = re-solve each row's
-    least-squares problem) and ``dtype`` (torch.float32 = the reference's
+    least-squares problem by Householder QR, "ls_gram" = the same residual
+    through per-row Gram matrices, much faster) and ``dtype`` (torch.float32 = the reference's
     precision, torch.float64).
 
     ``alpha``: the reference passes alpha to update()/reward() but reads the
