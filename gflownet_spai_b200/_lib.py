@@ -27,7 +27,7 @@ EXPORTS = [
     "spai_reward_from_taken_dev", "spai_row_index_sets", "spai_ls_solve_values_host",
     "spai_residual_pair_host", "spai_sample_step_dev", "spai_pack_taken_dev", "spai_reward_rows_dev", "spai_finalize_rewards_dev",
     "spai_ctx_enable_timing",
-    "spai_ctx_last_timing",
+    "spai_ctx_last_timing", "spai_ctx_set_deletion_hint",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     lib.spai_reward_rows_dev.argtypes = [pv, pv, i64, i64, i64, i32, i32, i64, i64, pv, pv, pv]
     lib.spai_finalize_rewards_dev.argtypes = [pv, pv, pv, i64, dbl, i32, pv, pv, pv]
     lib.spai_pack_taken_dev.argtypes = [pv, pv, i64, i64, i64, pv, i64, pv, pv]
+    lib.spai_ctx_set_deletion_hint.argtypes = [pv, i64]
     lib.spai_ctx_enable_timing.argtypes = [pv, i32]
     lib.spai_ctx_last_timing.argtypes = [pv, C.POINTER(SpaiTiming)]
     for name in EXPORTS:

@@ -395,7 +395,7 @@ __global__ void k3_finalize_kernel(const double* __restrict__ partial, int npart
     if (nnz_out) nnz_out[b] = z;
     return;
   }
-  const double res = sqrt(s);
+  const double res = sqrt(s < 0.0 ? 0.0 : s);      // (the delta form of K3s can land a hair below zero; NaN stays NaN)
   const double flops = 2.0 * (double)z * n;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const double rr = (res0 != 0.0) ? res / res0 : inf;

@@ -14,6 +14,7 @@
 #include "k2_ls.cuh"
 #include "k2g_gram.cuh"
 #include "k3_copy.cuh"
+#include "k3s_sparse.cuh"
 #include "k4_sample.cuh"
 #include "spai_internal.cuh"
 
@@ -380,7 +381,9 @@ struct Carver {
 };
 static inline int64_t padded(int64_t bytes) { return round_up(bytes, 256) + 256; }
 
-constexpr unsigned int LS_FAIL_CAP = 1u << 18;   // (row, trajectory) tiles redone by the generic kernel
+constexpr unsigned int LS_FAIL_CAP = 1u << 18;
+constexpr int K3S_MAX_CHUNKS = 512;
+constexpr int64_t K3S_MIN_RATIO = 40;            // K3s when a trajectory deletes <= 1/40 of the candidates (measured crossover ~3 % on cfg2)   // (row, trajectory) tiles redone by the generic kernel
 
 struct EvalShape {       // launch geometry of one reward evaluation over Bc trajectories
   int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
@@ -452,7 +455,7 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     s.gy = (int)ceil_div(Bp, (int64_t)K3_THREADS * s.nt);
     const int target = sm_count * k3_blocks_per_sm(dtype, s.nt);     // one full wave
     s.gx = (int)std::max<int64_t>(1, std::min<int64_t>(plan.ntiles, std::max(1, target / s.gy)));
-    s.parts = s.gx;
+    s.parts = std::max(s.gx, K3S_MAX_CHUNKS);        // the deletion-driven kernel writes one partial row per word chunk
   } else {
     s.Bp = round_up(Bc, 32);
     const int64_t Bp = s.Bp;
@@ -581,7 +584,11 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   double* res2x = cv.take<double>(Bp);
   int nl = 0;
 
-  if (W > 0) {
+  // few deletions per trajectory: the deletion-driven kernel (K3s) works on the trajectory-major
+  // mask directly, no transposed copy needed
+  bool sparse = mode == SPAI_MODE_COPY && plan.sparse_ready && t_hint > 0 && t_hint * K3S_MIN_RATIO <= P.E && W > 0;
+  if (const char* v = getenv("SPAI_K3_SPARSE")) sparse = atoi(v) != 0 && mode == SPAI_MODE_COPY && plan.sparse_ready && W > 0;   // A/B switch
+  if (W > 0 && !sparse) {
     const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
     k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
     SPAI_CUDA(cudaGetLastError()); ++nl;
@@ -602,7 +609,31 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   bool use_extra = false;
   const unsigned int* fail_count_dev = nullptr;
   int parts = s.parts;
-  if (mode == SPAI_MODE_COPY) {
+  if (sparse) {
+    const int64_t w_lo = plan.sptr_host[row_lo] >> 5;
+    const int64_t w_hi = std::min<int64_t>(W, ((int64_t)plan.sptr_host[row_hi] + 31) >> 5);
+    const int64_t range = std::max<int64_t>(w_hi - w_lo, 1);
+    // ~4096 mask words (131 072 slots) per block: the slot metadata and (f, w) pairs of the range
+    // (~13 MB) stay in L2 while the batch sweeps it. Measured on cfg5 (W = 340 384 words, B = 4096):
+    // 4 chunks 32.9 ms, 16: 25.0, 64: 19.5, 128: 20.5, 512: 23.8; cfg2 (W = 16 384): 4 chunks best.
+    const int64_t want_chunks = std::max<int64_t>(1, std::min<int64_t>(K3S_MAX_CHUNKS, ceil_div(range, 4096)));
+    const int64_t chunk_words = round_up(ceil_div(range, want_chunks), 128);
+    const int chunks = (int)ceil_div(range, chunk_words);
+    const double base_sum = plan.base_prefix[row_hi] - plan.base_prefix[row_lo];
+    const dim3 grid((unsigned)Bc, (unsigned)chunks);
+    const int slot_lo = plan.sptr_host[row_lo], slot_hi = plan.sptr_host[row_hi];
+    const SlotMeta* meta = reinterpret_cast<const SlotMeta*>(plan.sl_meta);
+    if (dtype == SPAI_F32)
+      k3s_sparse_kernel<float><<<grid, K3S_THREADS, 0, st>>>(
+          meta, P.slot_col, plan.a_ptr, plan.a_col, reinterpret_cast<const Pair<float>*>(plan.sl_rec), mask, W,
+          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial);
+    else
+      k3s_sparse_kernel<double><<<grid, K3S_THREADS, 0, st>>>(
+          meta, P.slot_col, plan.a_ptr, plan.a_col, reinterpret_cast<const Pair<double>*>(plan.sl_rec), mask, W,
+          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial);
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+    parts = chunks;
+  } else if (mode == SPAI_MODE_COPY) {
     // tiles that intersect [row_lo, row_hi)
     const auto& tr = plan.tile_row_host;
     int t_lo = 0, t_n = plan.ntiles;
@@ -762,6 +793,7 @@ struct spai_ctx {
   double res0[2] = {0, 0};
   int64_t flops0 = 0;
   int64_t ws_limit = (int64_t)16 << 30;
+  int64_t deletion_hint = 0;            // for the taken-bitmask entry point (no action list to measure)
   Workspace ws;
   PhaseTimer pt;
   spai_timing last = {};
@@ -834,6 +866,62 @@ static int ensure_gram(spai_ctx* c, int dtype, cudaStream_t st) {
   }
   plan.bytes = ar.bytes;
   plan.gram_ready = true;
+  return SPAI_OK;
+}
+
+// K3s data: slot -> row map, slot-major (segment sum, contribution) pairs, prefix sums of the
+// all-kept row residuals. Built the first time a batch of short trajectories is scored in copy mode.
+static int ensure_sparse(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.sparse_ready) return SPAI_OK;
+  const HostPattern& hp = c->hp;
+  const int64_t n = c->P.n, E = c->P.E;
+  Arena& ar = c->plan_arena[dtype];
+  std::vector<SlotMeta> meta((size_t)std::max<int64_t>(E, 1));
+  int64_t off = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t sp = hp.sptr[i];
+    const int k = hp.sptr[i + 1] - sp;
+    for (int32_t s = sp; s < sp + k; ++s) {
+      const int32_t col = hp.slot_col[s];
+      const int rc = c->ha.ptr[col + 1] - c->ha.ptr[col];
+      if (rc > 65535 || k > 65535) { set_error("K3s: row too long (k = %d, nnz(A row) = %d)", k, rc); return SPAI_ERR_UNSUPPORTED; }
+      meta[s].sp = sp; meta[s].k = (uint16_t)k; meta[s].rc = (uint16_t)rc; meta[s].off = off;
+      off += rc;
+    }
+  }
+  SlotMeta* meta_dev = nullptr;
+  SPAI_TRY(ar.upload(&meta_dev, meta));
+  plan.sl_meta = meta_dev;
+  const unsigned blocks = (unsigned)ceil_div(std::max<int64_t>(n, 1), 128);
+  plan.base_prefix.assign((size_t)n + 1, 0.0);
+  if (dtype == SPAI_F32) {
+    Pair<float>* out = nullptr;
+    SPAI_TRY(ar.alloc(&out, off));
+    k3s_build_kernel<float><<<blocks, 128, 0, st>>>(reinterpret_cast<const Rec32*>(plan.rec_copy), plan.cptr, plan.c_col,
+                                                    plan.rhdr, c->P.slot_col, c->A.ptr, c->A.col, meta_dev, n, out);
+    plan.sl_rec = out;
+    std::vector<float> rb((size_t)std::max<int64_t>(n, 1));
+    SPAI_CUDA(cudaMemcpyAsync(rb.data(), plan.row_base, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    SPAI_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n; ++i) plan.base_prefix[i + 1] = plan.base_prefix[i] + (double)rb[i];
+  } else {
+    Pair<double>* out = nullptr;
+    SPAI_TRY(ar.alloc(&out, off));
+    k3s_build_kernel<double><<<blocks, 128, 0, st>>>(reinterpret_cast<const Rec64*>(plan.rec_copy), plan.cptr, plan.c_col,
+                                                     plan.rhdr, c->P.slot_col, c->A.ptr, c->A.col, meta_dev, n, out);
+    plan.sl_rec = out;
+    std::vector<double> rb((size_t)std::max<int64_t>(n, 1));
+    SPAI_CUDA(cudaMemcpyAsync(rb.data(), plan.row_base, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SPAI_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n; ++i) plan.base_prefix[i + 1] = plan.base_prefix[i] + rb[i];
+  }
+  SPAI_CUDA(cudaGetLastError());
+  SPAI_CUDA(cudaStreamSynchronize(st));
+  plan.sptr_host = hp.sptr.data();
+  plan.a_ptr = c->A.ptr; plan.a_col = c->A.col;
+  plan.bytes = ar.bytes;
+  plan.sparse_ready = true;
   return SPAI_OK;
 }
 
@@ -977,6 +1065,12 @@ int spai_ctx_set_workspace_limit(spai_ctx* c, int64_t bytes) {
   return SPAI_OK;
 }
 
+int spai_ctx_set_deletion_hint(spai_ctx* c, int64_t max_deletions) {
+  if (!c || max_deletions < 0) return SPAI_ERR_INVALID;
+  c->deletion_hint = max_deletions;
+  return SPAI_OK;
+}
+
 int spai_ctx_enable_timing(spai_ctx* c, int enable) {
   if (!c) return SPAI_ERR_INVALID;
   c->pt.on = enable != 0;
@@ -1096,6 +1190,12 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   const bool mask_only = kept_bytes_dev != nullptr;
   if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode != SPAI_MODE_COPY, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
+  const int64_t t_len = (src == FROM_TAKEN_DEV) ? c->deletion_hint : T;     // longest trajectory (0 = unknown)
+  {
+    const char* force = getenv("SPAI_K3_SPARSE");
+    const bool want = force ? atoi(force) != 0 : (t_len > 0 && t_len * K3S_MIN_RATIO <= c->P.E);
+    if (!mask_only && mode == SPAI_MODE_COPY && want) SPAI_TRY(ensure_sparse(c, dtype, st));
+  }
   const Plan& plan = c->plan[mask_only ? SPAI_F32 : dtype];
   const Pattern& P = c->P;
   const int64_t W = P.words();
@@ -1229,7 +1329,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
     SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
                         (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready, c->row_lo,
-                        c->row_hi, c->partial_only, src == FROM_TAKEN_DEV ? 0 : T));
+                        c->row_hi, c->partial_only, t_len));
     if (pt->on) cudaEventRecord(pt->ev[4], st);
     if (out_host) {
       if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));

@@ -145,6 +145,14 @@ struct Plan {
   int32_t* rest_rows[LS_NCLASS] = {};
   int64_t rest_count[LS_NCLASS] = {};
   std::vector<int32_t> rest_rows_host[LS_NCLASS];
+  // deletion-driven copy kernel (K3s, built on first use)
+  bool sparse_ready = false;
+  void* sl_meta = nullptr;                           // SlotMeta[E]: row slot range + the slot's (f, w) list
+  void* sl_rec = nullptr;                            // Pair<T>[nc] slot-major
+  std::vector<double> base_prefix;                   // [n+1] prefix sums of row_base
+  const int32_t* sptr_host = nullptr;                // [n+1] host copy of the slot offsets (owned by the context)
+  const int32_t* a_ptr = nullptr;                    // CSR of A (owned by the context)
+  const int32_t* a_col = nullptr;
   double g_bytes_full = 0;        // SURVEY §8d G with every candidate kept (bytes / pattern)
   int64_t bytes = 0;
 };

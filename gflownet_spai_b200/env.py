@@ -119,6 +119,11 @@ class SpaiContext:
     def set_workspace_limit(self, nbytes: int):
         check(self._lib.spai_ctx_set_workspace_limit(self._h, int(nbytes)), "set_workspace_limit")
 
+    def set_deletion_hint(self, max_deletions: int):
+        """Upper bound on the edges one trajectory removes, for reward_from_taken (which sees
+        no action list): short trajectories then take the deletion-driven kernel. 0 = unknown."""
+        check(self._lib.spai_ctx_set_deletion_hint(self._h, int(max_deletions)), "set_deletion_hint")
+
     def enable_timing(self, on: bool = True):
         check(self._lib.spai_ctx_enable_timing(self._h, int(on)), "enable_timing")
 
@@ -323,10 +328,12 @@ class PreconditionerEnv(Env):
         actions = actions.to(torch.int64)
         return self.ctx.reward_batch(actions, self._alpha(alpha), self.mode, self.dtype, want)
 
-    def update_from_taken(self, taken: torch.Tensor, alpha):
+    def update_from_taken(self, taken: torch.Tensor, alpha, max_deletions: int = 0):
         """Batch reward straight from the sampler's device-resident taken-bitmask
         (int32 [B, words], edge order, bit set = edge removed): no action lists,
-        no host round trip."""
+        no host round trip. `max_deletions` (optional) bounds the edges a trajectory
+        removes; it only lets the library pick the kernel for short trajectories."""
+        self.ctx.set_deletion_hint(int(max_deletions))
         return self.ctx.reward_from_taken(taken, self._alpha(alpha), self.mode, self.dtype)
 
     def update(self, sparse_matrices, actions, alpha) -> list:

@@ -200,7 +200,7 @@ class GFlowNet(nn.Module):
         if method == "gumbel":
             complete_actions, taken = self._sample_gumbel(logits, bsz, dev, generator)
             al = float(alpha.detach()) if isinstance(alpha, torch.Tensor) else float(alpha)
-            rewards = self.env.update_from_taken(taken, al)["reward"]
+            rewards = self.env.update_from_taken(taken, al, max_deletions=complete_actions.shape[1])["reward"]
             if log is not None:
                 log._actions = complete_actions.t().contiguous().cpu()
                 log._fwd_probs = self.chosen_probs(p, complete_actions.to(p.device))
@@ -229,7 +229,7 @@ class GFlowNet(nn.Module):
         complete_actions = actions_tb.t().contiguous()            # [B, T] on the device
         al = float(alpha.detach()) if isinstance(alpha, torch.Tensor) else float(alpha)
         # the taken-bitmask IS the final state: score it directly (skips the actions -> mask kernel)
-        rewards = self.env.update_from_taken(taken, al)["reward"]
+        rewards = self.env.update_from_taken(taken, al, max_deletions=t_len)["reward"]
         if log is not None:
             log._actions = actions_tb.cpu()
             log._fwd_probs = self.chosen_probs(p, complete_actions.to(p.device))

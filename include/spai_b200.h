@@ -96,6 +96,12 @@ int spai_ctx_info(const spai_ctx* ctx, spai_info* out);
  * larger batches are processed in trajectory chunks. Default 16 GiB. */
 int spai_ctx_set_workspace_limit(spai_ctx* ctx, int64_t bytes);
 
+/* Upper bound on the number of edges one trajectory removes, for the entry point that
+ * carries no action list (spai_reward_from_taken_dev): lets the library pick the
+ * deletion-driven kernel for short trajectories. 0 (default) = unknown. The bound only
+ * selects a kernel; results do not depend on it. */
+int spai_ctx_set_deletion_hint(spai_ctx* ctx, int64_t max_deletions);
+
 /* PreconditionerEnv.update (preconditioner.py:32-52) for a whole batch:
  * actions int64[B, T] with leading dimension `ld` (>= T), -1 padded; ids outside
  * [0, E) — the terminal id included — match no edge (gflownet/utils.py:323).

@@ -3,8 +3,8 @@
 Usage (GPU box): python tools/ab_k3.py [cfg] [batch] [delete_fraction]
 Builds the problem once, draws `batch` trajectories that delete about
 `delete_fraction` of the candidate edges each (ids drawn with replacement:
-duplicates are legal input), and times reward_batch with the variant forced
-through SPAI_K3_COMPACT=0/1 and with the host's own choice.
+duplicates are legal input), and times reward_batch with the kernel forced
+through SPAI_K3_COMPACT=0/1 / SPAI_K3_SPARSE=0/1 and with the host's own choice.
 """
 import os
 import sys
@@ -36,11 +36,13 @@ def main():
     acts = torch.randint(0, e, (batch, t), generator=g, device="cuda", dtype=torch.int64)
     ctx.enable_timing(True)
     ref = None
-    for label, env in (("dense-variant", "0"), ("compact-variant", "1"), ("auto", None)):
-        if env is None:
-            os.environ.pop("SPAI_K3_COMPACT", None)
-        else:
-            os.environ["SPAI_K3_COMPACT"] = env
+    for label, env, sparse in (("dense-variant", "0", "0"), ("compact-variant", "1", "0"),
+                               ("deletion-driven (K3s)", None, "1"), ("auto", None, None)):
+        for key, val in (("SPAI_K3_COMPACT", env), ("SPAI_K3_SPARSE", sparse)):
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
         for _ in range(2):
             out = ctx.reward_batch(acts, 0.5, mode="copy", dtype=torch.float32)
         torch.cuda.synchronize()
