@@ -126,7 +126,8 @@ k3s_sparse_kernel(const SlotMeta* __restrict__ meta, const int32_t* __restrict__
                   const int32_t* __restrict__ a_ptr, const int32_t* __restrict__ a_col,
                   const Pair<T>* __restrict__ sl_rec, const uint32_t* __restrict__ mask, int64_t W,
                   int64_t B, int64_t Bp, int64_t w_lo, int64_t w_hi, int64_t chunk_words,
-                  int slot_lo, int slot_hi, double base_sum, double* __restrict__ partial) {
+                  int slot_lo, int slot_hi, double base_sum, double* __restrict__ partial,
+                  long long* __restrict__ nnz) {
   __shared__ int32_t light[K3S_THREADS / 32][K3S_LIST];
   __shared__ int32_t xs1[K3S_THREADS / 32][K3S_XCAP], xs2[K3S_THREADS / 32][K3S_XCAP];
   __shared__ double wsum[K3S_THREADS / 32];
@@ -140,6 +141,7 @@ k3s_sparse_kernel(const SlotMeta* __restrict__ meta, const int32_t* __restrict__
   int32_t* X2 = xs2[warp];
   int nl = 0, nx = 0;                                 // warp-uniform list fills
   double tot = 0.0;
+  int ones = 0;                                       // kept slots seen by this lane (nnz(M), when asked)
 
   // the pairs of deleted slots that share a row are rare and long (a merge of two rows of A):
   // they are queued and run 32 at a time so they never stall a pass of short single deltas
@@ -221,6 +223,7 @@ k3s_sparse_kernel(const SlotMeta* __restrict__ meta, const int32_t* __restrict__
     uint32_t z = (w < c_hi) ? ~mrow[w] : 0u;
     // exclusive prefix of the per-lane zero-bit counts
     const int cnt = __popc(z);
+    if (w < c_hi) ones += 32 - cnt;                   // the bits past E in the last word are zero
     int pre = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -253,6 +256,10 @@ k3s_sparse_kernel(const SlotMeta* __restrict__ meta, const int32_t* __restrict__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
   if (lane == 0) wsum[warp] = tot;
+  if (nnz) {                                          // integer atomics: order-independent
+    ones = __reduce_add_sync(0xffffffffu, ones);
+    if (lane == 0 && ones) atomicAdd(reinterpret_cast<unsigned long long*>(nnz + b), (unsigned long long)ones);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = (blockIdx.y == 0) ? base_sum : 0.0;

@@ -593,8 +593,12 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
     SPAI_CUDA(cudaGetLastError()); ++nl;
   }
+  // K3s reads every mask word anyway: over the full row range it also counts the kept slots
+  const bool count_in_k3s = sparse && !nnz_ready && row_lo == 0 && row_hi == plan.n;
   if (nnz_ready) {
     SPAI_CUDA(cudaMemcpyAsync(nnz, nnz_ready, (size_t)Bc * 8, cudaMemcpyDeviceToDevice, st));   // popcount fused into K0
+  } else if (count_in_k3s) {
+    SPAI_CUDA(cudaMemsetAsync(nnz, 0, (size_t)Bp * 8, st));
   } else {
     k0_popcount_kernel<<<(unsigned)Bc, 256, 0, st>>>(mask, W, Bc, nnz);
     SPAI_CUDA(cudaGetLastError()); ++nl;
@@ -626,11 +630,11 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     if (dtype == SPAI_F32)
       k3s_sparse_kernel<float><<<grid, K3S_THREADS, 0, st>>>(
           meta, P.slot_col, plan.a_ptr, plan.a_col, reinterpret_cast<const Pair<float>*>(plan.sl_rec), mask, W,
-          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial);
+          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial, count_in_k3s ? nnz : nullptr);
     else
       k3s_sparse_kernel<double><<<grid, K3S_THREADS, 0, st>>>(
           meta, P.slot_col, plan.a_ptr, plan.a_col, reinterpret_cast<const Pair<double>*>(plan.sl_rec), mask, W,
-          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial);
+          Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial, count_in_k3s ? nnz : nullptr);
     SPAI_CUDA(cudaGetLastError()); ++nl;
     parts = chunks;
   } else if (mode == SPAI_MODE_COPY) {
