@@ -15,6 +15,7 @@
 #include "k2g_gram.cuh"
 #include "k3_copy.cuh"
 #include "k3s_sparse.cuh"
+#include "k3t_lut.cuh"
 #include "k4_sample.cuh"
 #include "spai_internal.cuh"
 
@@ -434,6 +435,13 @@ static GramVariant gram_variant(int dtype, int g) {
   return {32, 8, GramGeom<double, 32, true>::RB, GramDist<double, 32, 8>::SMEM};
 }
 
+// ls_gram mode through the (row, kept-mask) table (K3t) instead of the Gram class-0 kernel
+static inline bool ls_table_on(const Plan& p) {
+  if (!p.lut_ls_ready) return false;
+  const char* v = getenv("SPAI_K3_LUT");            // A/B switch shared with copy mode
+  return !v || atoi(v) != 0;
+}
+
 // row list of QR class c: in ls_gram mode only the rows no Gram class takes
 static inline int64_t ls_count(const Plan& p, int mode, int c) {
   return mode == SPAI_MODE_LS_GRAM ? p.rest_count[c] : p.class_count[c];
@@ -458,11 +466,24 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
     s.parts = std::max(s.gx, K3S_MAX_CHUNKS);        // the deletion-driven kernel writes one partial row per word chunk
   } else {
     s.Bp = round_up(Bc, 32);
+    const bool ls_table = mode == SPAI_MODE_LS_GRAM && ls_table_on(plan);
+    if (ls_table) {                                  // the lookup kernel reads 128*NT mask columns per block
+      s.nt = (Bc >= 1024) ? 8 : (Bc >= 512 ? 4 : (Bc >= 256 ? 2 : 1));
+      if (dtype == SPAI_F64 && s.nt > 4) s.nt = 4;
+      s.Bp = round_up(Bc, (int64_t)K3_THREADS * s.nt);
+    }
     const int64_t Bp = s.Bp;
     s.parts = 0;
     if (mode == SPAI_MODE_LS_GRAM) {
       for (int g = 0; g < GRAM_NCLASS; ++g) {
         if (!plan.gram_count[g]) continue;
+        if (g == 0 && ls_table) {
+          s.has_column_class = true;
+          s.gram_gy[0] = (int)ceil_div(Bp, (int64_t)K3_THREADS * s.nt);
+          s.gram_gx[0] = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(plan.n, 16), std::max(1, sm_count * 6 / s.gram_gy[0])));
+          s.parts += s.gram_gx[0];
+          continue;
+        }
         const GramVariant v = gram_variant(dtype, g);
         s.has_column_class = true;                   // ill-conditioned tiles go to the generic kernel
         s.gram_gy[g] = (int)ceil_div(Bp, (int64_t)(K3_THREADS / v.lanes));
@@ -588,6 +609,8 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   // mask directly, no transposed copy needed
   bool sparse = mode == SPAI_MODE_COPY && plan.sparse_ready && t_hint > 0 && t_hint * K3S_MIN_RATIO <= P.E && W > 0;
   if (const char* v = getenv("SPAI_K3_SPARSE")) sparse = atoi(v) != 0 && mode == SPAI_MODE_COPY && plan.sparse_ready && W > 0;   // A/B switch
+  bool use_lut = mode == SPAI_MODE_COPY && !sparse && plan.lut_ready && W > 0;
+  if (const char* v = getenv("SPAI_K3_LUT")) use_lut = use_lut && atoi(v) != 0;               // A/B switch
   if (W > 0 && !sparse) {
     const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
     k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
@@ -637,6 +660,30 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
           Bc, Bp, w_lo, w_hi, chunk_words, slot_lo, slot_hi, base_sum, partial, count_in_k3s ? nnz : nullptr);
     SPAI_CUDA(cudaGetLastError()); ++nl;
     parts = chunks;
+  } else if (mode == SPAI_MODE_COPY && use_lut) {
+    // one full wave of blocks over (row ranges) x (128*NT trajectories)
+    const int64_t rows = row_hi - row_lo;
+    int gx = 1;
+    if (rows > 0) {
+      const int per_sm = std::max(1, (int)(200 * 1024 / (dtype == SPAI_F32 ? k3t_smem_bytes<float>() : k3t_smem_bytes<double>())));
+      gx = (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 16), (int64_t)std::max(1, sm_count * std::min(per_sm, 16) / s.gy),
+                                                       (int64_t)s.parts}));
+    }
+    const dim3 grid(gx, s.gy);
+#define SPAI_K3T(T, NT)                                                                                   \
+  k3t_lookup_kernel<T, NT><<<grid, K3_THREADS, k3t_smem_bytes<T>(), st>>>(reinterpret_cast<const T*>(plan.lut), \
+      plan.rhdr, maskT, Bp, W, partial, (int)row_lo, (int)row_hi)
+    if (rows <= 0) {
+      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st));
+    } else if (dtype == SPAI_F32) {
+      if (s.nt == 8) SPAI_K3T(float, 8); else if (s.nt == 4) SPAI_K3T(float, 4);
+      else if (s.nt == 2) SPAI_K3T(float, 2); else SPAI_K3T(float, 1);
+    } else {
+      if (s.nt == 4) SPAI_K3T(double, 4); else if (s.nt == 2) SPAI_K3T(double, 2); else SPAI_K3T(double, 1);
+    }
+#undef SPAI_K3T
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+    parts = gx;
   } else if (mode == SPAI_MODE_COPY) {
     // tiles that intersect [row_lo, row_hi)
     const auto& tr = plan.tile_row_host;
@@ -703,6 +750,24 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
       for (int g = 0; g < GRAM_NCLASS; ++g) {
         if (!plan.gram_count[g]) continue;
         double* pp = partial + (int64_t)off * Bp;
+        if (g == 0 && ls_table_on(plan)) {            // every (row, mask) residual is tabulated: look it up
+          const dim3 tgrid(s.gram_gx[0], s.gram_gy[0]);
+#define SPAI_K3TL(T, NT)                                                                                  \
+  k3t_lookup_kernel<T, NT, true><<<tgrid, K3_THREADS, k3t_smem_bytes<T>(), st>>>(reinterpret_cast<const T*>(plan.lut_ls), \
+      plan.rhdr, maskT, Bp, W, pp, (int)row_lo, (int)row_hi, Bc, fail_pairs, fail_count, LS_FAIL_CAP)
+          if (row_hi <= row_lo) {
+            SPAI_CUDA(cudaMemsetAsync(pp, 0, (size_t)s.gram_gx[0] * Bp * 8, st));
+          } else if (dtype == SPAI_F32) {
+            if (s.nt == 8) SPAI_K3TL(float, 8); else if (s.nt == 4) SPAI_K3TL(float, 4);
+            else if (s.nt == 2) SPAI_K3TL(float, 2); else SPAI_K3TL(float, 1);
+          } else {
+            if (s.nt == 4) SPAI_K3TL(double, 4); else if (s.nt == 2) SPAI_K3TL(double, 2); else SPAI_K3TL(double, 1);
+          }
+#undef SPAI_K3TL
+          SPAI_CUDA(cudaGetLastError());
+          off += s.gram_gx[0]; ++nl; any = true;
+          continue;
+        }
         int64_t roff, rcnt;
         sub(100 + g, &roff, &rcnt);
         const dim3 grid(s.gram_gx[g], s.gram_gy[g]);
@@ -870,6 +935,51 @@ static int ensure_gram(spai_ctx* c, int dtype, cudaStream_t st) {
   }
   plan.bytes = ar.bytes;
   plan.gram_ready = true;
+  return SPAI_OK;
+}
+
+// K3t table: every (row, kept-mask) residual of a pattern whose rows have <= 8 candidates.
+static int ensure_lut(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.lut_ready) return SPAI_OK;
+  const int64_t n = c->P.n;
+  if (n == 0 || c->P.max_k > K3T_K) return SPAI_OK;            // not applicable: the row sweep stays
+  Arena& ar = c->plan_arena[dtype];
+  if (dtype == SPAI_F32) {
+    float* t = nullptr;
+    SPAI_TRY(ar.alloc(&t, n * K3T_ENTRIES));
+    k3t_build_kernel<float><<<(unsigned)n, K3T_ENTRIES, 0, st>>>(reinterpret_cast<const Rec32*>(plan.rec_copy), plan.cptr, plan.rhdr, t);
+    plan.lut = t;
+  } else {
+    double* t = nullptr;
+    SPAI_TRY(ar.alloc(&t, n * K3T_ENTRIES));
+    k3t_build_kernel<double><<<(unsigned)n, K3T_ENTRIES, 0, st>>>(reinterpret_cast<const Rec64*>(plan.rec_copy), plan.cptr, plan.rhdr, t);
+    plan.lut = t;
+  }
+  SPAI_CUDA(cudaGetLastError());
+  plan.bytes = ar.bytes;
+  plan.lut_ready = true;
+  return SPAI_OK;
+}
+
+static int ensure_lut_ls(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.lut_ls_ready || !plan.gram_ready) return SPAI_OK;
+  const int64_t n = c->P.n;
+  if (n == 0 || c->P.max_k > K3T_K || !plan.gram_count[0]) return SPAI_OK;
+  Arena& ar = c->plan_arena[dtype];
+  const size_t w = dtype == SPAI_F32 ? 4 : 8;
+  unsigned char* t = nullptr;
+  SPAI_TRY(ar.alloc(&t, n * K3T_ENTRIES * (int64_t)w));
+  SPAI_CUDA(cudaMemsetAsync(t, 0, (size_t)n * K3T_ENTRIES * w, st));     // rows outside Gram class 0 add nothing here
+  if (dtype == SPAI_F32)
+    k3t_build_ls_kernel<float><<<(unsigned)plan.gram_count[0], K3T_ENTRIES, 0, st>>>(plan.gram[0], reinterpret_cast<float*>(t));
+  else
+    k3t_build_ls_kernel<double><<<(unsigned)plan.gram_count[0], K3T_ENTRIES, 0, st>>>(plan.gram[0], reinterpret_cast<double*>(t));
+  SPAI_CUDA(cudaGetLastError());
+  plan.lut_ls = t;
+  plan.bytes = ar.bytes;
+  plan.lut_ls_ready = true;
   return SPAI_OK;
 }
 
@@ -1194,6 +1304,8 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   const bool mask_only = kept_bytes_dev != nullptr;
   if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode != SPAI_MODE_COPY, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
+  if (!mask_only && mode == SPAI_MODE_LS_GRAM && B >= 64) SPAI_TRY(ensure_lut_ls(c, dtype, st));
+  if (!mask_only && mode == SPAI_MODE_COPY && B >= 64) SPAI_TRY(ensure_lut(c, dtype, st));
   const int64_t t_len = (src == FROM_TAKEN_DEV) ? c->deletion_hint : T;     // longest trajectory (0 = unknown)
   {
     const char* force = getenv("SPAI_K3_SPARSE");

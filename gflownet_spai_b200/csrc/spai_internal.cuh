@@ -145,6 +145,11 @@ struct Plan {
   int32_t* rest_rows[LS_NCLASS] = {};
   int64_t rest_count[LS_NCLASS] = {};
   std::vector<int32_t> rest_rows_host[LS_NCLASS];
+  // table-lookup copy kernel (K3t, rows with <= 8 candidates only; built on first use)
+  bool lut_ready = false;
+  void* lut = nullptr;                               // T[n][256]
+  bool lut_ls_ready = false;                         // the same for ls_gram mode (least-squares residuals)
+  void* lut_ls = nullptr;
   // deletion-driven copy kernel (K3s, built on first use)
   bool sparse_ready = false;
   void* sl_meta = nullptr;                           // SlotMeta[E]: row slot range + the slot's (f, w) list
