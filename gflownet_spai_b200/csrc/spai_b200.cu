@@ -437,7 +437,7 @@ static GramVariant gram_variant(int dtype, int g) {
 
 // ls_gram mode through the (row, kept-mask) table (K3t) instead of the Gram class-0 kernel
 static inline bool ls_table_on(const Plan& p) {
-  if (!p.lut_ls_ready) return false;
+  if (!p.lut_ls_ready || !p.tables_on) return false;
   const char* v = getenv("SPAI_K3_LUT");            // A/B switch shared with copy mode
   return !v || atoi(v) != 0;
 }
@@ -609,7 +609,7 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   // mask directly, no transposed copy needed
   bool sparse = mode == SPAI_MODE_COPY && plan.sparse_ready && t_hint > 0 && t_hint * K3S_MIN_RATIO <= P.E && W > 0;
   if (const char* v = getenv("SPAI_K3_SPARSE")) sparse = atoi(v) != 0 && mode == SPAI_MODE_COPY && plan.sparse_ready && W > 0;   // A/B switch
-  bool use_lut = mode == SPAI_MODE_COPY && !sparse && plan.lut_ready && W > 0;
+  bool use_lut = mode == SPAI_MODE_COPY && !sparse && plan.lut_ready && plan.tables_on && W > 0;
   if (const char* v = getenv("SPAI_K3_LUT")) use_lut = use_lut && atoi(v) != 0;               // A/B switch
   if (W > 0 && !sparse) {
     const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
@@ -944,6 +944,7 @@ static int ensure_lut(spai_ctx* c, int dtype, cudaStream_t st) {
   if (plan.lut_ready) return SPAI_OK;
   const int64_t n = c->P.n;
   if (n == 0 || c->P.max_k > K3T_K) return SPAI_OK;            // not applicable: the row sweep stays
+  if (n * K3T_ENTRIES * (dtype == SPAI_F32 ? 4 : 8) > ((int64_t)4 << 30)) return SPAI_OK;   // table cap: 4 GiB
   Arena& ar = c->plan_arena[dtype];
   if (dtype == SPAI_F32) {
     float* t = nullptr;
@@ -967,6 +968,7 @@ static int ensure_lut_ls(spai_ctx* c, int dtype, cudaStream_t st) {
   if (plan.lut_ls_ready || !plan.gram_ready) return SPAI_OK;
   const int64_t n = c->P.n;
   if (n == 0 || c->P.max_k > K3T_K || !plan.gram_count[0]) return SPAI_OK;
+  if (n * K3T_ENTRIES * (dtype == SPAI_F32 ? 4 : 8) > ((int64_t)4 << 30)) return SPAI_OK;
   Arena& ar = c->plan_arena[dtype];
   const size_t w = dtype == SPAI_F32 ? 4 : 8;
   unsigned char* t = nullptr;
@@ -987,7 +989,7 @@ static int ensure_lut_ls(spai_ctx* c, int dtype, cudaStream_t st) {
 // all-kept row residuals. Built the first time a batch of short trajectories is scored in copy mode.
 static int ensure_sparse(spai_ctx* c, int dtype, cudaStream_t st) {
   Plan& plan = c->plan[dtype];
-  if (plan.sparse_ready) return SPAI_OK;
+  if (plan.sparse_ready || plan.sparse_unavailable) return SPAI_OK;
   const HostPattern& hp = c->hp;
   const int64_t n = c->P.n, E = c->P.E;
   Arena& ar = c->plan_arena[dtype];
@@ -999,7 +1001,7 @@ static int ensure_sparse(spai_ctx* c, int dtype, cudaStream_t st) {
     for (int32_t s = sp; s < sp + k; ++s) {
       const int32_t col = hp.slot_col[s];
       const int rc = c->ha.ptr[col + 1] - c->ha.ptr[col];
-      if (rc > 65535 || k > 65535) { set_error("K3s: row too long (k = %d, nnz(A row) = %d)", k, rc); return SPAI_ERR_UNSUPPORTED; }
+      if (rc > 65535 || k > 65535) { plan.sparse_unavailable = true; return SPAI_OK; }   // the row sweep handles it
       meta[s].sp = sp; meta[s].k = (uint16_t)k; meta[s].rc = (uint16_t)rc; meta[s].off = off;
       off += rc;
     }
@@ -1306,6 +1308,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM && B >= 64) SPAI_TRY(ensure_lut_ls(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_COPY && B >= 64) SPAI_TRY(ensure_lut(c, dtype, st));
+  if (!mask_only) c->plan[dtype].tables_on = B >= 64;
   const int64_t t_len = (src == FROM_TAKEN_DEV) ? c->deletion_hint : T;     // longest trajectory (0 = unknown)
   {
     const char* force = getenv("SPAI_K3_SPARSE");

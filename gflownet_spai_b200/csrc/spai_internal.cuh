@@ -147,11 +147,14 @@ struct Plan {
   std::vector<int32_t> rest_rows_host[LS_NCLASS];
   // table-lookup copy kernel (K3t, rows with <= 8 candidates only; built on first use)
   bool lut_ready = false;
+  mutable bool tables_on = false;                    // set per call: tables serve calls with >= 64 trajectories, so the
+                                                     // kernel (and the rounding) a trajectory gets depends on the call alone
   void* lut = nullptr;                               // T[n][256]
   bool lut_ls_ready = false;                         // the same for ls_gram mode (least-squares residuals)
   void* lut_ls = nullptr;
   // deletion-driven copy kernel (K3s, built on first use)
   bool sparse_ready = false;
+  bool sparse_unavailable = false;                   // a row of A or of the pattern exceeds the SlotMeta fields
   void* sl_meta = nullptr;                           // SlotMeta[E]: row slot range + the slot's (f, w) list
   void* sl_rec = nullptr;                            // Pair<T>[nc] slot-major
   std::vector<double> base_prefix;                   // [n+1] prefix sums of row_base

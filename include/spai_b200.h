@@ -45,8 +45,10 @@ enum spai_mode {
   SPAI_MODE_LS_GRAM = 2 /* the same least-squares residual through the semi-normal
                          equations: the row's Gram matrix is formed once per
                          context, a (row, pattern) solve is a masked k x k LDL^T
-                         (rows with <= 8 candidates, <= 16 in fp32); other rows
-                         and ill-conditioned tiles go to the Householder kernels */
+                         (rows with <= 32 candidates; when every row has <= 8 the
+                         256 possible solves per row are tabulated once); other
+                         rows and ill-conditioned tiles go to the Householder
+                         kernels                                                 */
 };
 
 enum spai_dtype { SPAI_F32 = 0, SPAI_F64 = 1 };
@@ -69,7 +71,11 @@ typedef struct spai_info {
   int32_t has_duplicates;/* initial matrix has repeated coordinates                */
   int32_t device;
   int64_t rows_missing_diag; /* rows whose union index set misses the diagonal     */
-  int64_t ls_class_rows[8];  /* rows per ls kernel class (last = generic)          */
+  int64_t ls_class_rows[8];  /* rows per Householder kernel class of SPAI_MODE_LS, by
+                                (max candidates, max union size): [0..2] k<=8 with
+                                |I|<=18 / 20 / 40, [3..4] k<=16 with |I|<=52 / 64,
+                                [5..6] k<=32 with |I|<=52 / 64, [7] generic kernel
+                                (anything larger, rows with repeated coordinates)    */
   int64_t device_bytes;      /* bytes of device memory held by the context         */
 } spai_info;
 
