@@ -1,4 +1,4 @@
-"""Time the Householder (ls) and semi-normal-equation (ls_gram) reward modes on one
+"""Time reward modes (copy, ls = Householder, ls_gram = semi-normal equations) on one
 problem in one process and report how far apart their rewards are.
 
 Usage (GPU box): python tools/ab_ls.py [cfg] [batch] [modes,comma] [dtypes,comma]
@@ -35,15 +35,16 @@ def main():
         for md in modes:
             out = ctx.reward_batch(acts, 0.5, md, tdt)
             torch.cuda.synchronize()
-            ms = []
+            ms, tot = [], []
             for _ in range(3):
                 out = ctx.reward_batch(acts, 0.5, md, tdt)
                 torch.cuda.synchronize()
                 ms.append(ctx.last_timing().ms_reward)
+                tot.append(ctx.last_timing().ms_total)
             rw = out["reward"].cpu().numpy()
             base = ref.setdefault("f64" if "f64" in dtypes else dt, rw)
             err = float(np.max(np.abs(rw - base) / np.maximum(1e-300, np.abs(base))))
-            print(f"{md}/{dt}: reward kernels {np.median(ms):.3f} ms -> {batch * pb.n / np.median(ms) * 1e3:.3e} row solves/s; "
+            print(f"{md}/{dt}: whole step {np.median(tot):.3f} ms = {batch / np.median(tot) * 1e3:.3e} patterns/s; reward kernels {np.median(ms):.3f} ms -> {batch * pb.n / np.median(ms) * 1e3:.3e} row solves/s; "
                   f"max rel diff vs first f64 run {err:.2e}; nan={int(np.isnan(rw).sum())}", flush=True)
     ctx.close()
 
