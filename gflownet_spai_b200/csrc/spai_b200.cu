@@ -382,9 +382,9 @@ struct Carver {
 };
 static inline int64_t padded(int64_t bytes) { return round_up(bytes, 256) + 256; }
 
-constexpr unsigned int LS_FAIL_CAP = 1u << 18;
+constexpr unsigned int LS_FAIL_CAP = 1u << 18;   // (row, trajectory) tiles redone by the generic kernel
 constexpr int K3S_MAX_CHUNKS = 512;
-constexpr int64_t K3S_MIN_RATIO = 40;            // K3s when a trajectory deletes <= 1/40 of the candidates (measured crossover ~3 % on cfg2)   // (row, trajectory) tiles redone by the generic kernel
+constexpr int64_t K3S_MIN_RATIO = 40;            // K3s when a trajectory deletes <= 1/40 of the candidates (measured crossover ~3 % on cfg2)
 
 struct EvalShape {       // launch geometry of one reward evaluation over Bc trajectories
   int64_t Bp = 32;                                  // padded trajectory count (columns of maskT)
