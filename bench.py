@@ -391,7 +391,7 @@ def run_b200_arm(args):
             reward_kernel = "k3s_sparse_kernel"
         elif ctx.info().max_row_slots <= 8 and B >= 64:
             reward_kernel = "k3t_lookup_kernel"
-    elif args.mode == "ls_gram" and ctx.info().max_row_slots <= 8 and B >= 64:
+    elif args.mode in ("ls", "ls_gram") and ctx.info().max_row_slots <= 8 and B >= 64:
         reward_kernel = "k3t_lookup_kernel(ls table)"
     kern = {
         "k0_masks(actions->kept bitmask)": {"ms": ph["masks"], "algorithmic_bytes": k0_bytes},
@@ -466,9 +466,9 @@ def run_b200_arm(args):
     if rank == 0 and not args.no_extras and args.mode == "copy":
         for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("ls_gram", torch.float32),
                        ("ls_gram", torch.float64), ("copy", torch.float64)):
-            # the Householder kernels get a smaller batch (they are ~10x slower); Gram mode runs the whole batch
-            small = 1024 if args.config in ("cfg1", "cfg2") else 64
-            sub = acts[: min(B, small)] if md == "ls" or args.config not in ("cfg1", "cfg2") else acts
+            # cfg1/cfg2 (rows <= 8 candidates): every mode runs the whole batch through its table; larger
+            # patterns get a small batch (the Householder kernels are slow there)
+            sub = acts if args.config in ("cfg1", "cfg2") else acts[: min(B, 64)]
             try:
                 for _ in range(2):
                     ctx.reward_batch(sub, 0.5, md, dt)

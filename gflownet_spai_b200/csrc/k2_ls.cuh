@@ -434,7 +434,7 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
                      int64_t work_stride, int32_t* colmap, int64_t colmap_stride,
                      double* __restrict__ res2, const int2* __restrict__ pairs,
                      const unsigned int* __restrict__ npairs, unsigned int pair_cap,
-                     double* __restrict__ row_out) {
+                     double* __restrict__ row_out, int64_t row_out_ld = 1) {
   using Rec = typename RecOf<T>::type;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -512,7 +512,7 @@ k2_ls_generic_kernel(const typename RecOf<T>::type* __restrict__ recs,
     for (int r = p + lane; r < q; r += 32) r2 = fma(y[r], y[r], r2);
     r2 = k2_wsum(r2);
     if (lane == 0) {
-      if (row_out) row_out[i] = (double)r2;      // per-row mode (B == 1): all-kept baseline of the row
+      if (row_out) row_out[(int64_t)i * row_out_ld + b] = (double)r2;   // per-row mode: row_out[row][trajectory]
       else atomicAdd(res2 + b, (double)r2);
     }
     __syncwarp();

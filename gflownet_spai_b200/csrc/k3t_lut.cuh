@@ -62,6 +62,19 @@ k3t_build_ls_kernel(const unsigned char* __restrict__ gram, T* __restrict__ lut)
   lut[(int64_t)h.row * K3T_ENTRIES + m] = r2;
 }
 
+// Householder (`ls`) mode: the table is filled by the generic QR kernel itself, run on 256
+// pseudo-trajectories — pseudo-trajectory m keeps, in EVERY row, exactly the candidates whose bit is
+// set in m. This kernel writes that mask (transposed layout, Bp = 256 columns, zero-filled before).
+__global__ void k3t_uniform_masks_kernel(const int32_t* __restrict__ sptr, int64_t n, uint32_t* __restrict__ maskT) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = idx >> K3T_K;
+  const uint32_t m = (uint32_t)(idx & (K3T_ENTRIES - 1));
+  if (row >= n) return;
+  const int sp = sptr[row], k = sptr[row + 1] - sp;
+  for (int j = 0; j < k && j < K3T_K; ++j)
+    if ((m >> j) & 1u) atomicOr(&maskT[(int64_t)((sp + j) >> 5) * K3T_ENTRIES + m], 1u << ((sp + j) & 31));
+}
+
 template <typename T, int NT, bool FAILS = false>
 __global__ void __launch_bounds__(K3_THREADS)
 k3t_lookup_kernel(const T* __restrict__ lut, const RowHdr* __restrict__ rhdr,

@@ -442,6 +442,13 @@ static inline bool ls_table_on(const Plan& p) {
   return !v || atoi(v) != 0;
 }
 
+// ls mode through the Householder-filled table (covers every row when rows have <= 8 candidates)
+static inline bool qr_table_on(const Plan& p) {
+  if (!p.lut_qr_ready || !p.tables_on) return false;
+  const char* v = getenv("SPAI_K3_LUT");
+  return !v || atoi(v) != 0;
+}
+
 // row list of QR class c: in ls_gram mode only the rows no Gram class takes
 static inline int64_t ls_count(const Plan& p, int mode, int c) {
   return mode == SPAI_MODE_LS_GRAM ? p.rest_count[c] : p.class_count[c];
@@ -467,6 +474,14 @@ static EvalShape plan_shape(const Plan& plan, int mode, int dtype, int64_t Bc, i
   } else {
     s.Bp = round_up(Bc, 32);
     const bool ls_table = mode == SPAI_MODE_LS_GRAM && ls_table_on(plan);
+    if (mode == SPAI_MODE_LS && qr_table_on(plan)) {          // one lookup kernel, nothing else
+      s.nt = (Bc >= 512) ? 4 : (Bc >= 256 ? 2 : 1);
+      s.Bp = round_up(Bc, (int64_t)K3_THREADS * s.nt);
+      s.gy = (int)ceil_div(s.Bp, (int64_t)K3_THREADS * s.nt);
+      s.gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(plan.n, 16), std::max(1, sm_count * 6 / s.gy)));
+      s.parts = s.gx;
+      return s;
+    }
     if (ls_table) {                                  // the lookup kernel reads 128*NT mask columns per block
       s.nt = (Bc >= 1024) ? 8 : (Bc >= 512 ? 4 : (Bc >= 256 ? 2 : 1));
       if (dtype == SPAI_F64 && s.nt > 4) s.nt = 4;
@@ -727,6 +742,18 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     }
 #undef SPAI_K3
     SPAI_CUDA(cudaGetLastError()); ++nl;
+  } else if (mode == SPAI_MODE_LS && qr_table_on(plan)) {
+    const dim3 tgrid(s.gx, s.gy);
+    if (row_hi <= row_lo) {
+      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st));
+      parts = 1;
+    } else {
+      if (s.nt == 4) k3t_lookup_kernel<double, 4><<<tgrid, K3_THREADS, k3t_smem_bytes<double>(), st>>>(plan.lut_qr, plan.rhdr, maskT, Bp, W, partial, (int)row_lo, (int)row_hi);
+      else if (s.nt == 2) k3t_lookup_kernel<double, 2><<<tgrid, K3_THREADS, k3t_smem_bytes<double>(), st>>>(plan.lut_qr, plan.rhdr, maskT, Bp, W, partial, (int)row_lo, (int)row_hi);
+      else k3t_lookup_kernel<double, 1><<<tgrid, K3_THREADS, k3t_smem_bytes<double>(), st>>>(plan.lut_qr, plan.rhdr, maskT, Bp, W, partial, (int)row_lo, (int)row_hi);
+      SPAI_CUDA(cudaGetLastError()); ++nl;
+      parts = s.gx;
+    }
   } else {
     if (!plan.rec_ls) { set_error("plan was built without ls records"); return SPAI_ERR_INVALID; }
     int2* fail_pairs = nullptr;
@@ -982,6 +1009,54 @@ static int ensure_lut_ls(spai_ctx* c, int dtype, cudaStream_t st) {
   plan.lut_ls = t;
   plan.bytes = ar.bytes;
   plan.lut_ls_ready = true;
+  return SPAI_OK;
+}
+
+// ls (Householder) mode table: the generic QR kernel evaluated on the 256 uniform masks.
+static int ensure_lut_qr(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.lut_qr_ready || !plan.rec_ls) return SPAI_OK;
+  const int64_t n = c->P.n;
+  if (n == 0 || c->P.max_k > K3T_K || n * K3T_ENTRIES * 8 > ((int64_t)4 << 30)) return SPAI_OK;
+  Arena& ar = c->plan_arena[dtype];
+  SPAI_TRY(ar.alloc(&plan.lut_qr, n * K3T_ENTRIES));
+  SPAI_CUDA(cudaMemsetAsync(plan.lut_qr, 0, (size_t)n * K3T_ENTRIES * 8, st));
+  std::vector<int32_t> live;
+  for (int cl = 0; cl < LS_NCLASS; ++cl) live.insert(live.end(), plan.class_rows_host[cl].begin(), plan.class_rows_host[cl].end());
+  if (!live.empty()) {
+    Arena tmp;
+    int32_t* live_dev = nullptr;
+    SPAI_TRY(tmp.upload(&live_dev, live));
+    const int64_t W = std::max<int64_t>(c->P.words(), 1), Bp = K3T_ENTRIES;
+    uint32_t* masks = nullptr;
+    SPAI_TRY(tmp.alloc(&masks, W * Bp));
+    SPAI_CUDA(cudaMemsetAsync(masks, 0, (size_t)W * Bp * 4, st));
+    k3t_uniform_masks_kernel<<<(unsigned)ceil_div(n * K3T_ENTRIES, 256), 256, 0, st>>>(c->P.sptr, n, masks);
+    SPAI_CUDA(cudaGetLastError());
+    const int64_t warps = (int64_t)c->sm_count * 16;
+    const int64_t wstride = std::max<int64_t>(plan.max_q, 1) * ((int64_t)c->P.max_k + 1);
+    int32_t* cmap = nullptr;
+    SPAI_TRY(tmp.alloc(&cmap, warps * std::max<int64_t>(c->P.max_k, 1)));
+    if (dtype == SPAI_F32) {
+      float* work = nullptr;
+      SPAI_TRY(tmp.alloc(&work, warps * wstride));
+      k2_ls_generic_kernel<float><<<(unsigned)(warps / 4), 128, 0, st>>>(
+          reinterpret_cast<const Rec32*>(plan.rec_ls), plan.cptr, c->P.sptr, plan.r_q, plan.r_diag, live_dev,
+          (int64_t)live.size(), masks, Bp, K3T_ENTRIES, work, wstride, cmap, std::max<int64_t>(c->P.max_k, 1), nullptr,
+          nullptr, nullptr, 0u, plan.lut_qr, K3T_ENTRIES);
+    } else {
+      double* work = nullptr;
+      SPAI_TRY(tmp.alloc(&work, warps * wstride));
+      k2_ls_generic_kernel<double><<<(unsigned)(warps / 4), 128, 0, st>>>(
+          reinterpret_cast<const Rec64*>(plan.rec_ls), plan.cptr, c->P.sptr, plan.r_q, plan.r_diag, live_dev,
+          (int64_t)live.size(), masks, Bp, K3T_ENTRIES, work, wstride, cmap, std::max<int64_t>(c->P.max_k, 1), nullptr,
+          nullptr, nullptr, 0u, plan.lut_qr, K3T_ENTRIES);
+    }
+    SPAI_CUDA(cudaGetLastError());
+    SPAI_CUDA(cudaStreamSynchronize(st));            // scratch of tmp is released on return
+  }
+  plan.bytes = ar.bytes;
+  plan.lut_qr_ready = true;
   return SPAI_OK;
 }
 
@@ -1307,6 +1382,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode != SPAI_MODE_COPY, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM && B >= 64) SPAI_TRY(ensure_lut_ls(c, dtype, st));
+  if (!mask_only && mode == SPAI_MODE_LS && B >= 64) SPAI_TRY(ensure_lut_qr(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_COPY && B >= 64) SPAI_TRY(ensure_lut(c, dtype, st));
   if (!mask_only) c->plan[dtype].tables_on = B >= 64;
   const int64_t t_len = (src == FROM_TAKEN_DEV) ? c->deletion_hint : T;     // longest trajectory (0 = unknown)

@@ -152,6 +152,8 @@ struct Plan {
   void* lut = nullptr;                               // T[n][256]
   bool lut_ls_ready = false;                         // the same for ls_gram mode (least-squares residuals)
   void* lut_ls = nullptr;
+  bool lut_qr_ready = false;                         // ls mode: filled by the Householder kernel, always f64[n][256]
+  double* lut_qr = nullptr;
   // deletion-driven copy kernel (K3s, built on first use)
   bool sparse_ready = false;
   bool sparse_unavailable = false;                   // a row of A or of the pattern exceeds the SlotMeta fields

@@ -155,3 +155,26 @@ def test_ls_gram_table_hands_dependent_columns_to_householder():
         ref = ctx.reward_batch(torch.from_numpy(acts).cuda(), 0.5, "ls_gram", torch.float64)
     assert torch.allclose(got["residual"], ref["residual"], rtol=1e-9, atol=1e-9)
     ctx.close()
+
+
+def test_householder_table_matches_householder_kernels_and_oracle():
+    """ls mode, >= 64 trajectories, rows with <= 8 candidates: the table is filled by the generic
+    Householder kernel on the 256 uniform masks; same numbers as the register QR kernels."""
+    p = synth.make_problem("cfg2", 0.125)
+    ctx = _ctx(p)
+    acts = synth.make_trajectories(p.num_edges, 70, seed0=15)
+    t = torch.from_numpy(acts).cuda()
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-5)):
+        got = ctx.reward_batch(t, 0.5, "ls", dtype)
+        with _env(SPAI_K3_LUT="0"):
+            ref = ctx.reward_batch(t, 0.5, "ls", dtype)
+        assert torch.allclose(got["residual"], ref["residual"], rtol=tol, atol=1e-12)
+        assert torch.equal(got["nnz_m"], ref["nnz_m"])
+    got = ctx.reward_batch(t, 0.5, "ls", torch.float64)
+    wls = orc.reward_batch_ls(p.n, p.edge_row, p.edge_col, p.a, acts[:2], 0.5, dtype=np.float64, baseline_dtype=np.float64)
+    np.testing.assert_allclose(got["reward"].cpu().numpy()[:2], wls["reward"], rtol=1e-10, atol=1e-7)
+    part, nnz = ctx.reward_rows(t, 100, 700, "ls", torch.float64)
+    with _env(SPAI_K3_LUT="0"):
+        part_ref, _ = ctx.reward_rows(t, 100, 700, "ls", torch.float64)
+    assert torch.allclose(part, part_ref, rtol=1e-11, atol=1e-12)
+    ctx.close()
