@@ -463,7 +463,7 @@ def run_b200_arm(args):
 
     # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
     extras = {}
-    if rank == 0 and not args.no_extras and args.mode == "copy":
+    if rank == 0 and world == 1 and not args.no_extras and args.mode == "copy":
         for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("ls_gram", torch.float32),
                        ("ls_gram", torch.float64), ("copy", torch.float64)):
             # cfg1/cfg2 (rows <= 8 candidates): every mode runs the whole batch through its table; larger
@@ -486,7 +486,7 @@ def run_b200_arm(args):
             except Exception as exc:        # report, never hide
                 extras[f"{md}/{dt}"] = {"error": str(exc)}
 
-    if rank == 0 and not args.no_extras and args.mode == "copy":
+    if rank == 0 and world == 1 and not args.no_extras and args.mode == "copy":
         # early-training regime: short trajectories (64 deletions) -> most rows untouched -> incremental path
         try:
             g = torch.Generator(device=dev)
