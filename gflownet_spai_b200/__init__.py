@@ -7,7 +7,7 @@ include/spai_b200.h; these modules are the host-side mirror of the reference's
 Python interface.
 """
 from .env import Data, Env, PreconditionerEnv, SpaiContext, residual_pair  # noqa: F401
-from .sampler import GFlowNet, Log, trajectory_balance_loss  # noqa: F401
+from .sampler import BackwardPolicy, GFlowNet, Log, trajectory_balance_loss  # noqa: F401
 
 __all__ = ["Data", "Env", "PreconditionerEnv", "SpaiContext", "residual_pair", "GFlowNet", "Log",
-           "trajectory_balance_loss"]
+           "trajectory_balance_loss", "BackwardPolicy"]

@@ -26,7 +26,7 @@ from torch import nn
 
 from .env import Data
 
-__all__ = ["GFlowNet", "Log", "trajectory_balance_loss"]
+__all__ = ["GFlowNet", "Log", "trajectory_balance_loss", "BackwardPolicy"]
 
 
 def trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs):
@@ -45,6 +45,47 @@ def trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs):
     lhs = torch.log(total_flow + eps) + lf
     rhs = torch.log(rewards + eps) + lb
     return ((lhs - rhs) ** 2).mean()
+
+
+class BackwardPolicy(nn.Module):
+    """Drop-in for the reference's backward policy (policy.py:75-129) with the per-trajectory
+    Python loop replaced by ONE packed LSTM call over the batch.
+
+    Same constructor, same parameter names (`lstm`, `fc`: a reference state_dict loads
+    as is), same output: for trajectory b with `len_b` valid (non -1) leading entries,
+    softmax of the first `len_b` outputs of `fc(h_last)` followed by ones up to the
+    maximum length; shape [B, 1, T] like the reference's stack of [1, T] rows.
+    The reference feeds each action id as a 1-feature float sequence (`input_dim` must be 1).
+    """
+
+    def __init__(self, input_dim: int, hidden_dim: int, max_num_actions: int):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.max_num_actions = max_num_actions
+        self.lstm = nn.LSTM(input_dim, hidden_dim, batch_first=True)
+        self.fc = nn.Linear(hidden_dim, max_num_actions)
+
+    def forward(self, trajectories: torch.Tensor) -> torch.Tensor:
+        bsz, max_len = trajectories.shape
+        lengths = (trajectories != -1).sum(dim=1)                     # policy.py:96-100 (valid prefix)
+        if bool((lengths == 0).any()):
+            raise RuntimeError("BackwardPolicy: a trajectory has no valid action "
+                               "(the reference fails in pack_padded_sequence for length 0)")
+        packed = nn.utils.rnn.pack_padded_sequence(trajectories.float().unsqueeze(-1), lengths.cpu(),
+                                                   batch_first=True, enforce_sorted=False)
+        out, _ = self.lstm(packed)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True)      # [B, max(len), H]
+        idx = (lengths - 1).to(out.device).view(-1, 1, 1).expand(bsz, 1, out.size(2))
+        last = out.gather(1, idx).squeeze(1)                                  # hidden state at the last valid step
+        logits = self.fc(last)                                                # [B, max_num_actions]
+        width = min(max_len, self.max_num_actions)
+        pos = torch.arange(width, device=logits.device)[None, :]
+        valid = pos < lengths.to(logits.device)[:, None]                      # slice [:len_b] (policy.py:119)
+        probs = torch.softmax(logits[:, :width].masked_fill(~valid, float("-inf")), dim=1)
+        probs = torch.where(valid, probs, torch.ones_like(probs))             # pad with 1 (policy.py:125)
+        if width < max_len:
+            probs = torch.nn.functional.pad(probs, (0, max_len - width), value=1.0)
+        return probs.unsqueeze(1)
 
 
 class Log:
