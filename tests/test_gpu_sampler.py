@@ -196,3 +196,42 @@ def test_gumbel_whole_trajectory_sampler(small_env):
     loss = trajectory_balance_loss(log.total_flow, log.rewards.clamp_min(1e-3), log.fwd_probs, log.back_probs)
     loss.backward()
     assert torch.isfinite(fp.logit.grad).all()
+
+
+def test_training_step_with_batched_backward_policy_and_ls_gram_rewards():
+    """The loop of the reference's train.py / GFlowNet100.py:285-310 on the drop-in classes:
+    sample a batch on the device, least-squares rewards, batched LSTM backward policy,
+    trajectory-balance loss, one optimiser step on both policies."""
+    from gflownet_spai_b200.env import PreconditionerEnv
+    from gflownet_spai_b200.sampler import BackwardPolicy, GFlowNet, trajectory_balance_loss
+    p = synth.make_problem("cfg1")
+    init = torch.sparse_coo_tensor(torch.tensor(np.stack([p.edge_row, p.edge_col])),
+                                   torch.tensor(p.edge_val, dtype=torch.float32), (p.n, p.n))
+    env = PreconditionerEnv(p.n, init, init.clone(), mode="ls_gram", dtype=torch.float64)
+    fp = _StubForward(env.num_actions)
+    with torch.no_grad():
+        fp.logit[-1] = 4.0
+    bp = BackwardPolicy(1, 8, env.num_actions)
+    model = GFlowNet(fp, bp, env)
+    opt = torch.optim.Adam(list(fp.parameters()) + list(bp.parameters()), lr=1e-2)
+    s0 = [init.clone() for _ in range(64)]
+    losses = []
+    for it in range(2):
+        log = model.sample_states(s0, return_log=True, method="gumbel",
+                                  generator=torch.Generator(device="cuda").manual_seed(10 + it))
+        assert log.back_probs.shape == log.fwd_probs.shape
+        loss = trajectory_balance_loss(log.total_flow, log.rewards.clamp_min(1e-3), log.fwd_probs, log.back_probs)
+        opt.zero_grad()
+        loss.backward()
+        assert all(torch.isfinite(q.grad).all() for q in list(fp.parameters()) + list(bp.parameters()) if q.grad is not None)
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses))
+    # ls rewards never below copy rewards for the same trajectories (smaller residual)
+    acts = log.actions.t().contiguous()
+    r_ls = torch.tensor(env.update(s0, acts, 0.5), dtype=torch.float64)
+    env_copy = PreconditionerEnv(p.n, init, init.clone(), mode="copy", dtype=torch.float64)
+    r_cp = torch.tensor(env_copy.update(s0, acts, 0.5), dtype=torch.float64)
+    assert torch.all(r_ls >= r_cp - 1e-6)
+    env.ctx.close()
+    env_copy.ctx.close()
