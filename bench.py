@@ -49,16 +49,33 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=96, help="trajectories in the CPU-baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip the ls-mode side measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 block of the JSON line")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5", help="side configs measured after the headline")
+    ap.add_argument("--cfg5-batch", type=int, default=16384, help="cfg5 global batch (strong-scaled over the ranks)")
+    ap.add_argument("--no-lengths", action="store_true",
+                    help="headline without caller-supplied row lengths (the kernels then stream the -1 padding too)")
     ap.add_argument("--max-frac", type=float, default=0.0,
-                    help="trajectory b deletes floor(u_b*E*max_frac) edges (0 = 0.5; cfg5: 0.01)")
+                    help="trajectory b deletes floor(u_b*E*max_frac) edges (0 = 0.5, SURVEY 8d)")
     return ap.parse_args()
 
 
-def workload_name(args, p, batch):
-    desc = {"cfg1": "2-D Poisson 10x10", "cfg2": "2-D 5-pt Poisson 256x256", "cfg3": "3-D 7-pt Poisson 64^3",
-            "cfg4": "2-D convection-diffusion 512x512", "cfg5": "banded+power-law n=1M"}[args.config]
-    return (f"{args.config}: {desc} n={p.n} E={p.num_edges} (<= {p.k}/row), B={batch}/GPU, "
-            f"{args.mode}/{args.dtype}")
+CFG_DESC = {"cfg1": "2-D Poisson 10x10", "cfg2": "2-D 5-pt Poisson 256x256", "cfg3": "3-D 7-pt Poisson 64^3",
+            "cfg4": "2-D convection-diffusion 512x512", "cfg5": "banded+power-law n=1M"}
+
+
+def workload_name(cfg, p, batch, mode, dtype):
+    return f"{cfg}: {CFG_DESC[cfg]} n={p.n} E={p.num_edges} (<= {p.k}/row), B={batch}/GPU, {mode}/{dtype}"
+
+
+def config_dict(args, p, batch, world, max_frac):
+    """The SAME dict on both arms (b200 and reference): static facts of the workload only."""
+    return {"workload": workload_name(args.config, p, batch, args.mode, args.dtype), "mode": args.mode, "n": p.n,
+            "num_edges": p.num_edges, "batch_per_gpu": batch, "alpha": 0.5, "max_deleted_fraction": max_frac,
+            "trajectories": "SURVEY 8d: trajectory b deletes floor(u_b*E*max_deleted_fraction) distinct edges "
+                            "(torch.randperm, seed 1000+b), then the terminal id; int64 [B, T], -1 padded",
+            "parallelism": f"trajectory-sharded x{world}",
+            "l2": "256 MiB flush between timed iterations; actions exceed L2",
+            "timing": "CUDA events per step on the launch stream, max over ranks"}
 
 
 # ---------------------------------------------------------------------------
@@ -129,6 +146,9 @@ class ClockSampler:
 # synthetic trajectories on the device (seeded per global trajectory index)
 # ---------------------------------------------------------------------------
 def device_trajectories(num_edges, batch, first, device, max_frac=0.5):
+    """(actions int64[batch, T], lengths int32[batch]) on the device; trajectory `first + b` is seeded
+    1000 + first + b (a shard of a batch equals the same rows of the full batch). lengths[b] counts the
+    deleted edges and the terminal id; the rest of the row is -1 padding."""
     import torch
     lens = []
     gens = []
@@ -145,7 +165,35 @@ def device_trajectories(num_edges, batch, first, device, max_frac=0.5):
         if t:
             acts[b, :t] = torch.randperm(num_edges, generator=gens[b], device=device)[:t]
         acts[b, t] = num_edges
-    return acts
+    return acts, torch.tensor([t + 1 for t in lens], dtype=torch.int32, device=device)
+
+
+def pin_to_gpu_numa_node(index):
+    """Pin this process (and so its pinned allocations and the library's host threads) to the CPUs of the
+    GPU's NUMA node: at N > 1 every rank then streams its actions out of socket-local memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+    return None
 
 
 def measured_peak():
@@ -231,15 +279,53 @@ def cpu_port_throughput(cfg, scale, sample, procs):
     return per * procs / dt, dt
 
 
+def reference_itself(p, sample):
+    """patterns/s of the UNMODIFIED reference (`PreconditionerEnv.update`, preconditioner.py:32-52, staged
+    under baseline/_ref by __graft_entry__.build()): as is (gc.collect() after every trajectory, :51) and
+    with gc.collect patched out (SURVEY 8d items i / ii). None when the staged copy is absent."""
+    import gc
+    try:
+        import torch
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            return None
+        from gflownet_spai_b200 import synth
+        coo = p.a.tocoo()
+        acts = synth.make_trajectories(p.num_edges, sample)
+        torch.set_num_threads(os.cpu_count() or 1)
+        out = {"threads": torch.get_num_threads(), "sample": f"{sample} trajectories of the workload",
+               "source": ref_shim.REFERENCE_ROOT}
+        t0 = time.perf_counter()
+        ref_shim.reference_update(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, acts, 0.5)
+        out["as_is_patterns_per_s"] = sample / (time.perf_counter() - t0)
+        real = gc.collect
+        mods = [m for m in ref_shim.load_reference().modules if hasattr(m, "gc")]
+        try:
+            for m in mods:
+                m.gc = type("NoGc", (), {"collect": staticmethod(lambda *a, **k: 0)})
+            t0 = time.perf_counter()
+            ref_shim.reference_update(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, acts, 0.5)
+            out["minus_gc_patterns_per_s"] = sample / (time.perf_counter() - t0)
+        finally:
+            for m in mods:
+                m.gc = gc
+            gc.collect = real
+        return out
+    except Exception as exc:            # report, never hide
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     from gflownet_spai_b200 import synth
     p = synth.make_problem(args.config, args.scale)
     batch = args.batch or p.batch
+    max_frac = args.max_frac or 0.5
     per_step = max(procs, min(args.cpu_sample, 4 * procs))
     vals = []
     import multiprocessing as mp
@@ -257,12 +343,14 @@ def run_reference_arm(args):
     value = per * procs * args.steps / total
     sample = (f"each step = {per * procs} trajectories of the workload (of B={batch}) over {procs} processes; "
               "numpy/scipy restatement of the reference's update() (no gc.collect, no Python set loop)")
+    itself = reference_itself(p, 3 if p.n > 10000 else 16) if args.mode == "copy" else None
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-        "data": "synthetic", "config": {"workload": workload_name(args, p, batch)},
+        "data": "synthetic", "config": config_dict(args, p, batch, world, max_frac),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "reference_itself": itself,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -292,6 +380,168 @@ def algorithmic_bytes(ctx, p, acts_dev, mode, wbytes):
     return total + 8.0 * acts_dev.shape[0]
 
 
+def reward_kernel_name(ctx, p, mode, B, tmax):
+    """Which reward kernel the library picks for this call (mirrors eval_masks in spai_b200.cu)."""
+    k = ctx.info().max_row_slots
+    if mode == "copy":
+        if tmax * 40 <= p.num_edges:
+            return "k3s_sparse_kernel"
+        return "k3t_lookup_kernel" if (k <= 8 and B >= 64) else "k3_copy_kernel"
+    if k <= 8 and B >= 64:
+        return "k3t_lookup_kernel(ls table)"
+    return KNAMES[mode]
+
+
+def mask_kernel_name(p):
+    return "k0_mask_build_smem_kernel" if (p.num_edges + 31) // 32 * 4 <= 100 * 1024 else "k0b_sort_kernel+k0b_build_kernel"
+
+
+def phase_times(ctx, call, flush, nrep):
+    """Per-phase CUDA-event times of the library (masks / transpose+popcount / reward kernel / finalize), ms."""
+    ctx.enable_timing(True)
+    ph = {"masks": 0.0, "transpose": 0.0, "reward": 0.0, "finalize": 0.0}
+    for _ in range(nrep):
+        flush.zero_()
+        call()
+        tm = ctx.last_timing()
+        ph["masks"] += tm.ms_masks / nrep
+        ph["transpose"] += tm.ms_transpose / nrep
+        ph["reward"] += tm.ms_reward / nrep
+        ph["finalize"] += tm.ms_finalize / nrep
+    ctx.enable_timing(False)
+    return ph
+
+
+def oracle_check(p, acts_rows, got_reward, mode, dtype):
+    """In-run parity: timed trajectories re-scored by the CPU oracle (copy mode; ls on small n)."""
+    from oracle import spai_oracle as orc
+    npdt = np.float32 if dtype == "f32" else np.float64
+    if mode == "copy":
+        want = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val.astype(npdt), p.a.astype(npdt),
+                                     acts_rows, 0.5, dtype=npdt)["reward"]
+    elif p.n <= 70000:
+        want = orc.reward_batch_ls(p.n, p.edge_row, p.edge_col, p.a, acts_rows, 0.5, dtype=npdt,
+                                   baseline_dtype=npdt)["reward"]
+    else:
+        return None
+    err = np.abs(got_reward - want) / np.maximum(np.abs(want), 1e-12)
+    return {"trajectories": int(acts_rows.shape[0]), "max_rel_err_vs_oracle": float(np.max(err)),
+            "tolerance": 1e-4 if dtype == "f32" else 1e-10}
+
+
+def side_config(name, args, rank, world, dev, local, flush, peak):
+    """One entry of the `configs` block: a BASELINE config other than the headline, measured on this
+    rank's shard with the same rules (warm-up, CUDA events, inputs larger than L2 / L2 flush, max over
+    ranks), per-kernel shares, compulsory-byte fraction and an in-run oracle check.
+      cfg3  B = 4096 per GPU (weak, trajectory-sharded), copy/fp32
+      cfg4  B = 1024 per GPU (weak), copy fp32 + fp64 and ls_gram fp64
+      cfg5  B = 16 384 GLOBAL, strong-scaled (16 384 / N per rank), copy/fp32, SURVEY 8d trajectories"""
+    import torch
+    import torch.distributed as dist
+    from gflownet_spai_b200 import synth
+    from gflownet_spai_b200.env import SpaiContext
+
+    t_host = time.perf_counter()
+    p = synth.make_problem(name, args.scale)
+    coo = p.a.tocoo()
+    ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, device=local)
+    setup_s = time.perf_counter() - t_host
+    e = p.num_edges
+    W = (e + 31) // 32
+    strong = name == "cfg5"
+    if strong:
+        total = max(world, int(args.cfg5_batch * min(1.0, args.scale * args.scale)) if args.scale < 1 else args.cfg5_batch)
+        lo, hi = rank * total // world, (rank + 1) * total // world
+    else:
+        per = args.batch or {"cfg3": 4096, "cfg4": 1024}.get(name, p.batch)
+        if args.scale < 1:
+            per = max(64, int(per * args.scale))
+        total, lo, hi = per * world, rank * per, (rank + 1) * per
+    variants = [("copy", "f32")]
+    if name == "cfg4":
+        variants += [("copy", "f64"), ("ls_gram", "f64")]
+    # trajectory chunks that fit next to the workspace (int64 [chunk, T], T up to E/2 + 1)
+    tmax_bound = e // 2 + 2
+    chunk = max(32, min(hi - lo, int((40 << 30) // (8 * tmax_bound)) // 32 * 32))
+    res = {"n": p.n, "num_edges": e, "global_batch": total, "batch_this_rank": hi - lo,
+           "scaling": "strong" if strong else "weak", "chunk_trajectories": chunk, "setup_s": setup_s,
+           "mask_kernel": mask_kernel_name(p), "variants": {}}
+    tot_ms = {v: 0.0 for v in variants}
+    ph_acc = {v: None for v in variants}
+    valid_ids = 0
+    tmax_seen = 0
+    parity = {}
+    first = True
+    gen_s = 0.0
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        tg = time.perf_counter()
+        acts, lens = device_trajectories(e, c1 - c0, c0, dev, 0.5)
+        torch.cuda.synchronize()
+        gen_s += time.perf_counter() - tg
+        valid_ids += int(lens.sum())
+        tmax_seen = max(tmax_seen, int(acts.shape[1]))
+        for (mode, dt) in variants:
+            tdt = torch.float32 if dt == "f32" else torch.float64
+            sub, sl = acts, lens
+            if mode == "ls_gram" and name == "cfg4":          # ~0.4 s per 1024 patterns: time a 256-pattern slice
+                sub, sl = acts[:256], lens[:256]
+            call = lambda: ctx.reward_batch(sub, 0.5, mode, tdt, want=("reward",), lengths=sl)
+            if first:                                          # warm-up: plans, tables, workspace, clocks
+                for _ in range(2):
+                    out = call()
+                torch.cuda.synchronize()
+                if rank == 0 and mode == "copy":
+                    try:
+                        parity[f"{mode}/{dt}"] = oracle_check(p, sub[:1].cpu().numpy(), out["reward"][:1].cpu().numpy(), mode, dt)
+                    except Exception as exc:
+                        parity[f"{mode}/{dt}"] = {"error": f"{type(exc).__name__}: {exc}"}
+                ph_acc[(mode, dt)] = phase_times(ctx, call, flush, 2)
+            reps = 3 if not strong else 1
+            ms = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                call()
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1) / reps
+            scale_up = (acts.shape[0] / sub.shape[0])
+            tot_ms[(mode, dt)] += ms * scale_up
+        first = False
+        del acts, lens
+    for (mode, dt) in variants:
+        t = torch.tensor([tot_ms[(mode, dt)]], dtype=torch.float64, device=dev)
+        ids = torch.tensor([float(valid_ids)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ids, op=dist.ReduceOp.SUM)
+        ms = float(t)
+        ph = ph_acc[(mode, dt)] or {}
+        comp = float(ids) * 8.0 + total * (W * 4.0 + 8.0)
+        k0_bytes_rank = valid_ids * 8.0 + (hi - lo) * W * 4.0
+        share_tot = max(sum(ph.values()), 1e-9) if ph else 1.0
+        k0_ms_rank = tot_ms[(mode, dt)] * (ph.get("masks", 0.0) / share_tot) if ph else None
+        res["variants"][f"{mode}/{dt}"] = {
+            "ms_per_step": ms, "patterns_per_s": total / (ms / 1e3), "row_solves_per_s": total * p.n / (ms / 1e3),
+            "kernel_share": {k: v / share_tot for k, v in ph.items()} if ph else None,
+            "reward_kernel": reward_kernel_name(ctx, p, mode, min(chunk, hi - lo), tmax_seen),
+            "compulsory_bytes_per_step": comp, "compulsory_frac_of_hbm_peak": comp / (ms / 1e3) / 1e9 / peak,
+            "k0_valid_bytes_gbps": (k0_bytes_rank / (k0_ms_rank / 1e3) / 1e9) if k0_ms_rank else None,
+            "k0_frac_of_hbm_peak_on_valid_bytes": (k0_bytes_rank / (k0_ms_rank / 1e3) / 1e9 / peak) if k0_ms_rank else None,
+            "note": ("ls_gram timed on 256 of every 1024 patterns and scaled" if (mode == "ls_gram" and name == "cfg4") else None),
+        }
+    res["max_trajectory_len"] = tmax_seen
+    res["trajectory_generation_s_untimed"] = gen_s
+    res["parity_check"] = parity or None
+    res["l2"] = "inputs per call (valid ids * 8 B) exceed L2; 256 MiB flush between timed calls"
+    ctx.close()
+    del ctx
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -305,6 +555,7 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tdtype = torch.float32 if args.dtype == "f32" else torch.float64
@@ -316,14 +567,16 @@ def run_b200_arm(args):
     t0 = time.perf_counter()
     ctx = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, device=local)
     setup_s = time.perf_counter() - t0
-    max_frac = args.max_frac or (0.01 if args.config == "cfg5" else 0.5)
-    acts = device_trajectories(p.num_edges, batch, rank * batch, dev, max_frac)     # weak scaling: B per GPU
+    max_frac = args.max_frac or 0.5
+    acts, lens = device_trajectories(p.num_edges, batch, rank * batch, dev, max_frac)     # weak scaling: B per GPU
     B, T = acts.shape
+    use_len = None if args.no_lengths else lens
+    valid_ids = int(lens.sum())
     gathered = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)         # > 126 MB L2
 
     def step_dev():
-        out = ctx.reward_batch(acts, 0.5, args.mode, tdtype)
+        out = ctx.reward_batch(acts, 0.5, args.mode, tdtype, lengths=use_len)
         if world > 1 and not os.environ.get("SPAI_BENCH_NO_GATHER"):
             dist.all_gather_into_tensor(gathered, out["reward"])
         return out
@@ -358,7 +611,7 @@ def run_b200_arm(args):
                   "samples": sum(c["samples"] for c in allc if c), "per_rank_sm_mhz": [c["sm_mhz"] if c else None for c in allc]}
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     if os.environ.get("SPAI_BENCH_DEBUG"):
-        print(f"[rank {rank}] T={T} valid={int((acts >= 0).sum())} clocks={clocks}", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] T={T} valid={valid_ids} clocks={clocks}", file=sys.stderr, flush=True)
         print(f"[rank {rank}] per-step ms: {[round(a.elapsed_time(b), 3) for a, b in ev]}", file=sys.stderr, flush=True)
     launches = ctx.last_timing().launches * args.steps
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -368,58 +621,49 @@ def run_b200_arm(args):
     value = world * B * args.steps / (dev_ms / 1e3)
 
     # ---- per-kernel share + roofline (timing pass, device-resident inputs)
-    ctx.enable_timing(True)
-    ph = {"masks": 0.0, "transpose": 0.0, "reward": 0.0, "finalize": 0.0}
     nrep = max(3, min(args.steps, 10))
-    for _ in range(nrep):
-        flush.zero_()
-        ctx.reward_batch(acts, 0.5, args.mode, tdtype)
-        tm = ctx.last_timing()
-        ph["masks"] += tm.ms_masks / nrep
-        ph["transpose"] += tm.ms_transpose / nrep
-        ph["reward"] += tm.ms_reward / nrep
-        ph["finalize"] += tm.ms_finalize / nrep
-    ctx.enable_timing(False)
-    g_bytes = algorithmic_bytes(ctx, p, acts, args.mode, wbytes) if rank == 0 else 0.0
+    ph = phase_times(ctx, lambda: ctx.reward_batch(acts, 0.5, args.mode, tdtype, lengths=use_len), flush, nrep)
     W = (p.num_edges + 31) // 32
-    k0_bytes = float(B) * T * 8 + 2.0 * B * W * 4
+    read_ids = float(valid_ids) if use_len is not None else float(B) * T
+    k0_bytes = read_ids * 8 + float(B) * W * 4            # ids streamed once + the bitmask written once
+    k0_bytes_padded = float(B) * T * 8 + float(B) * W * 4  # what a caller without row lengths makes K0 read
     peak, peak_src = measured_peak()
-    # which reward kernel the library picks for this workload (mirrors eval_masks in spai_b200.cu)
-    reward_kernel = KNAMES[args.mode]
-    if args.mode == "copy":
-        if T * 40 <= p.num_edges:
-            reward_kernel = "k3s_sparse_kernel"
-        elif ctx.info().max_row_slots <= 8 and B >= 64:
-            reward_kernel = "k3t_lookup_kernel"
-    elif args.mode in ("ls", "ls_gram") and ctx.info().max_row_slots <= 8 and B >= 64:
-        reward_kernel = "k3t_lookup_kernel(ls table)"
-    kern = {
-        "k0_masks(actions->kept bitmask)": {"ms": ph["masks"], "algorithmic_bytes": k0_bytes},
-        "k0_transpose+popcount": {"ms": ph["transpose"], "algorithmic_bytes": 3.0 * B * W * 4},
-        reward_kernel: {"ms": ph["reward"], "algorithmic_bytes": g_bytes},
-        "k3_finalize": {"ms": ph["finalize"], "algorithmic_bytes": 16.0 * B},
-    }
-    for v in kern.values():
-        v["gbps"] = v["algorithmic_bytes"] / max(v["ms"], 1e-9) / 1e6
-        v["share"] = v["ms"] / max(sum(ph.values()), 1e-9)
+    reward_kernel = reward_kernel_name(ctx, p, args.mode, B, T)
+    mask_kernel = mask_kernel_name(p)
     info0 = ctx.info()
     rec_bytes = 16.0 * info0.contributions + 16.0 * p.n
-    kname = reward_kernel
-    kern[kname]["compulsory_bytes"] = float(B) * W * 4 + rec_bytes + 8.0 * B      # masks once + plan once + sums
-    kern[kname]["compulsory_gbps"] = kern[kname]["compulsory_bytes"] / max(kern[kname]["ms"], 1e-9) / 1e6
+    table = reward_kernel.startswith("k3t") or reward_kernel.startswith("k3s")
+    reward_comp = float(B) * W * 4 + 8.0 * B + (p.n * 256.0 * wbytes if reward_kernel.startswith("k3t") else rec_bytes)
+    kern = {
+        f"k0_masks({mask_kernel}: actions->kept bitmask)": {"ms": ph["masks"], "algorithmic_bytes": k0_bytes,
+                                                             "padded_bytes": k0_bytes_padded},
+        "k0_transpose+popcount": {"ms": ph["transpose"], "algorithmic_bytes": 2.0 * B * W * 4},
+        reward_kernel: {"ms": ph["reward"], "algorithmic_bytes": reward_comp,
+                        "bytes_kind": "compulsory HBM bytes (kept-mask words once + table/plan once + sums)"},
+        "k3_finalize": {"ms": ph["finalize"], "algorithmic_bytes": 16.0 * B},
+    }
+    if not table and rank == 0:
+        # row-sweep / solve kernels: SURVEY 8d gather-inclusive G (exceeds DRAM traffic by the batch re-use)
+        kern[reward_kernel]["gather_inclusive_G_bytes"] = algorithmic_bytes(ctx, p, acts, args.mode, wbytes)
+        kern[reward_kernel]["G_gbps"] = kern[reward_kernel]["gather_inclusive_G_bytes"] / max(ph["reward"], 1e-9) / 1e6
+    for v in kern.values():
+        v["gbps"] = v["algorithmic_bytes"] / max(v["ms"], 1e-9) / 1e6
+        v["frac_of_hbm_peak"] = v["gbps"] / peak
+        v["share"] = v["ms"] / max(sum(ph.values()), 1e-9)
     dom = max(kern, key=lambda k: kern[k]["ms"])
+    step_bytes = k0_bytes + 8.0 * B
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbps"] / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "frac": kern[dom]["gbps"] / peak, "traffic": ncu_traffic(dom.split("(")[0] if dom.startswith("k0_masks") else dom),
+                "peak_source": peak_src,
                 "launch_ms": kern[dom]["ms"], "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
-                "compulsory_bytes_per_launch": kern[dom].get("compulsory_bytes"),
-                "compulsory_frac": (kern[dom]["compulsory_gbps"] / peak) if "compulsory_gbps" in kern[dom] else None,
+                "padded_bytes_per_launch": kern[dom].get("padded_bytes"),
+                "whole_step_compulsory_frac": step_bytes / (dev_ms / args.steps / 1e3) / 1e9 / peak,
                 "ncu": _ncu_side_facts(dom),
-                "note": "algorithmic bytes = SURVEY.md 8d gather-inclusive G (every gathered entry of A for every "
-                        "pattern). The reward kernels re-use the gathered row data across the patterns of a CTA (K3: "
-                        "records staged in shared memory; K3t: every (row, kept-mask) residual tabulated once per "
-                        "context), so their G/time exceeds the HBM peak by design and their compulsory HBM traffic is "
-                        "compulsory_bytes_per_launch. For k0_masks the algorithmic bytes are real DRAM bytes: "
-                        "B*T*8 action bytes read + the bitmask written."}
+                "note": "k0_masks: algorithmic bytes = the VALID action ids (sum_b T_b * 8 B; row lengths are passed, so "
+                        "the -1 padding is never read) + the bitmask written once (B*W*4). Reward kernels: compulsory "
+                        "HBM bytes (masks + table/plan once); their gather-inclusive G (SURVEY 8d) is printed "
+                        "separately for the row-sweep kernels only, because the batch re-uses every gathered row from "
+                        "shared memory and G/time exceeds the HBM peak by design."}
 
     # ---- end to end through the host entry point (pinned host actions in, rewards out)
     e2e = None
@@ -428,6 +672,7 @@ def run_b200_arm(args):
         try:
             host = torch.empty((B, T), dtype=torch.int64, pin_memory=True)
             host.copy_(acts)
+            host_len = lens.cpu()
             torch.cuda.synchronize()
         except Exception as exc:        # pinned-memory pressure with many ranks: report, never hide
             ok, e2e = 0, {"error": f"{type(exc).__name__}: {exc}"}
@@ -436,57 +681,79 @@ def run_b200_arm(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = int(flag)
         if ok:
-            for _ in range(2):
-                r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0 = time.perf_counter()
-            e0.record()
-            for _ in range(args.steps):
-                r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",))   # syncs: result is on the host
+            e2e = {}
+            for key, hl in (("with_lengths", host_len), ("scan", None)):
+                if key == "with_lengths" and args.no_lengths:
+                    continue
+                for _ in range(2):
+                    r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",), lengths=hl)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                w0 = time.perf_counter()
+                e0.record()
+                nst = args.steps if key == "with_lengths" or args.no_lengths else max(2, args.steps // 4)
+                for _ in range(nst):
+                    r = ctx.reward_batch(host, 0.5, args.mode, tdtype, want=("reward",), lengths=hl)   # syncs: result on the host
+                    if world > 1:
+                        dist.all_gather_into_tensor(gathered, r["reward"].to(dev))
+                e1.record()
+                barrier()
+                e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
+                t_e = torch.tensor([e_ms], dtype=torch.float64, device=dev)
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered, r["reward"].to(dev))
-            e1.record()
-            barrier()
-            e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
-            t_e = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * B * args.steps / (float(t_e) / 1e3), "unit": UNIT,
-                   "h2d_bytes_per_step": int(ctx.last_timing().h2d_bytes), "d2h_bytes_per_step": int(B * 8),
-                   "input_bytes_per_step": int(B * T * 8), "ms_per_step": float(t_e) / args.steps,
-                   "api": "SpaiContext.reward_batch(pinned host int64 actions[B,T]) -> spai_reward_batch_host; "
-                          "the -1 padding of every row is trimmed on the host, so h2d_bytes < input bytes"}
+                    dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+                e2e[key] = {"value": world * B * nst / (float(t_e) / 1e3), "ms_per_step": float(t_e) / nst,
+                            "h2d_bytes_per_step": int(ctx.last_timing().h2d_bytes), "steps": nst}
+            head = e2e.get("with_lengths") or e2e["scan"]
+            e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": int(B * 8), "input_bytes_per_step": int(B * T * 8),
+                   "ms_per_step": head["ms_per_step"], "per_gpu_value": head["value"] / world,
+                   "h2d_gbps_per_gpu": head["h2d_bytes_per_step"] / head["ms_per_step"] / 1e6,
+                   "variants": e2e, "numa": numa,
+                   "api": "SpaiContext.reward_batch(pinned host int64 actions[B,T], lengths=int32[B]) -> "
+                          "spai_reward_batch_host_len: the valid prefix of every row streams over PCIe straight into "
+                          "the mask kernel (zero-copy), nothing on the host touches the data; variant 'scan' = the "
+                          "plain reference call without lengths (worker threads find the -1 padding)"}
         elif e2e is None:
             e2e = {"error": "pinned host allocation failed on another rank"}
         del host
 
-    # ---- ls-mode side measurements (north-star kernels K1/K2), not the headline
+    # ---- side measurements on the headline config (not the headline): other modes, padded input, int32 ids
     extras = {}
+
+    def timed(call, reps=3):
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            call()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
     if rank == 0 and world == 1 and not args.no_extras and args.mode == "copy":
         for md, dt in (("ls", torch.float32), ("ls", torch.float64), ("ls_gram", torch.float32),
                        ("ls_gram", torch.float64), ("copy", torch.float64)):
-            # cfg1/cfg2 (rows <= 8 candidates): every mode runs the whole batch through its table; larger
-            # patterns get a small batch (the Householder kernels are slow there)
-            sub = acts if args.config in ("cfg1", "cfg2") else acts[: min(B, 64)]
+            small = args.config in ("cfg1", "cfg2")
+            sub, sl = (acts, use_len) if small else (acts[: min(B, 64)], None if use_len is None else use_len[: min(B, 64)])
             try:
-                for _ in range(2):
-                    ctx.reward_batch(sub, 0.5, md, dt)
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(3):
-                    ctx.reward_batch(sub, 0.5, md, dt)
-                a1.record()
-                torch.cuda.synchronize()
-                ms = a0.elapsed_time(a1) / 3
+                ms = timed(lambda: ctx.reward_batch(sub, 0.5, md, dt, lengths=sl))
                 extras[f"{md}/{'f32' if dt == torch.float32 else 'f64'}"] = {
                     "patterns_per_s": sub.shape[0] / (ms / 1e3), "row_solves_per_s": sub.shape[0] * p.n / (ms / 1e3),
                     "batch": int(sub.shape[0]), "ms": ms}
             except Exception as exc:        # report, never hide
                 extras[f"{md}/{dt}"] = {"error": str(exc)}
-
-    if rank == 0 and world == 1 and not args.no_extras and args.mode == "copy":
+        try:
+            ms = timed(lambda: ctx.reward_batch(acts, 0.5, args.mode, tdtype))
+            extras["no row lengths (the -1 padding is streamed and ignored)"] = {"patterns_per_s": B / (ms / 1e3), "ms": ms}
+            a32 = acts.to(torch.int32)
+            ms = timed(lambda: ctx.reward_batch(a32, 0.5, args.mode, tdtype, lengths=lens))
+            extras["int32 ids + row lengths (device-resident sampler format)"] = {"patterns_per_s": B / (ms / 1e3), "ms": ms}
+            del a32
+        except Exception as exc:
+            extras["input formats"] = {"error": str(exc)}
         # early-training regime: short trajectories (64 deletions) -> most rows untouched -> incremental path
         try:
             g = torch.Generator(device=dev)
@@ -494,16 +761,7 @@ def run_b200_arm(args):
             short = torch.randint(0, p.num_edges, (B, 65), generator=g, device=dev, dtype=torch.int64)
             short[:, -1] = p.num_edges
             for md in ("copy", "ls", "ls_gram"):
-                for _ in range(2):
-                    ctx.reward_batch(short, 0.5, md, tdtype)
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(5):
-                    ctx.reward_batch(short, 0.5, md, tdtype)
-                a1.record()
-                torch.cuda.synchronize()
-                ms = a0.elapsed_time(a1) / 5
+                ms = timed(lambda: ctx.reward_batch(short, 0.5, md, tdtype), reps=5)
                 extras[f"{md}/{args.dtype} short trajectories (64 deletions, untouched rows skipped)"] = {
                     "patterns_per_s": B / (ms / 1e3), "batch": int(B), "ms": ms}
         except Exception as exc:
@@ -516,21 +774,14 @@ def run_b200_arm(args):
         # two of the timed trajectories re-scored by the oracle
         from oracle import spai_oracle as orc
         sel = acts[:2].cpu().numpy()
-        if args.mode == "copy":
-            npdt = np.float32 if args.dtype == "f32" else np.float64
-            want = orc.reward_batch_copy(p.n, p.edge_row, p.edge_col, p.edge_val.astype(npdt), p.a.astype(npdt),
-                                         sel, 0.5, dtype=npdt)["reward"]
-            got = ctx.reward_batch(acts[:2], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
-            parity = {"trajectories": 2, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
-        elif p.n <= 70000:
-            npdt = np.float32 if args.dtype == "f32" else np.float64
-            want = orc.reward_batch_ls(p.n, p.edge_row, p.edge_col, p.a, sel[:1], 0.5, dtype=npdt,
-                                       baseline_dtype=npdt)["reward"]
-            got = ctx.reward_batch(acts[:1], 0.5, args.mode, tdtype)["reward"].cpu().numpy()
-            parity = {"trajectories": 1, "max_rel_err_vs_oracle": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))}
+        nsel = 2 if args.mode == "copy" else 1
+        try:
+            got = ctx.reward_batch(acts[:nsel], 0.5, args.mode, tdtype, lengths=None if use_len is None else use_len[:nsel])
+            parity = oracle_check(p, sel[:nsel], got["reward"].cpu().numpy(), args.mode, args.dtype)
+        except Exception as exc:
+            parity = {"error": f"{type(exc).__name__}: {exc}"}
         # ls-mode CPU restatement (LAPACK lstsq per row), bounded sample: 2048 rows of one pattern
         try:
-            import scipy.sparse as _sp
             kept = orc.kept_edge_mask(p.num_edges, sel[0])
             pat = orc.build_pattern_matrix(p.n, p.edge_row, p.edge_col, np.ones(p.num_edges), kept, np.float64)
             rows_s = np.linspace(0, p.n - 1, num=min(p.n, 2048), dtype=np.int64)
@@ -546,19 +797,36 @@ def run_b200_arm(args):
         v, dt = cpu_port_throughput(args.config, args.scale, args.cpu_sample, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{args.cpu_sample} trajectories of the same workload, copy/fp32, numpy/scipy oracle "
-                         f"single process ({dt:.1f} s)"}
+                         f"single process ({dt:.1f} s); `--impl reference` runs the same port on all host cores"}
+
+    info = ctx.info()
+    ctx_bytes = int(info.device_bytes)
+    contributions, max_union = int(info.contributions), int(info.max_row_union)
+    class_rows = [int(x) for x in info.ls_class_rows]
+    ctx.close()
+    del ctx, acts, lens
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (each rank scores its shard; rank 0 reports)
+    configs = {}
+    if not args.no_configs:
+        for name in [c for c in args.configs.split(",") if c and c != args.config]:
+            try:
+                configs[name] = side_config(name, args, rank, world, dev, local, flush, peak)
+            except Exception as exc:        # report, never hide; keep the ranks in step
+                configs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                if world > 1:
+                    raise
 
     if rank == 0:
-        info = ctx.info()
+        cfg = config_dict(args, p, B, world, max_frac)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(args, p, B), "mode": args.mode, "n": p.n, "num_edges": p.num_edges,
-                       "batch_per_gpu": B, "max_trajectory_len": T, "alpha": 0.5, "max_deleted_fraction": max_frac,
-                       "parallelism": f"trajectory-sharded x{world}",
-                       "l2": "256 MiB flush between timed iterations; actions (B*T*8 B) exceed L2",
-                       "timing": "CUDA events per step on the launch stream, max over ranks"},
+            "config": cfg,
+            "workload_detail": {"max_trajectory_len": T, "valid_ids_per_step": valid_ids, "padded_ids_per_step": B * T,
+                                "row_lengths_passed": use_len is not None, "id_bytes": 8},
             "row_solves_per_s": value * p.n,
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "gpu_launches": int(launches),
@@ -569,12 +837,12 @@ def run_b200_arm(args):
             "cpu_baseline": cpu,
             "parity_check": parity,
             "extras": extras,
-            "context": {"setup_s": setup_s, "plan_contributions": int(info.contributions),
-                        "device_bytes": int(info.device_bytes), "max_row_union": int(info.max_row_union),
-                        "ls_class_rows": [int(x) for x in info.ls_class_rows]},
+            "configs": configs,
+            "context": {"setup_s": setup_s, "plan_contributions": contributions,
+                        "device_bytes": ctx_bytes, "max_row_union": max_union,
+                        "ls_class_rows": class_rows},
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

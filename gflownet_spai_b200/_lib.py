@@ -2,8 +2,7 @@
 
 The library is the product: there is no Python/CPU fallback. Loading fails
 loudly when the shared object is missing (build it with
-``python -c "import __graft_entry__ as g; g.build()"`` or
-``make -C gflownet_spai_b200/csrc``), and every call raises ``SpaiError`` /
+``python -c "import __graft_entry__ as g; g.build()"``), and every call raises ``SpaiError`` /
 ``ValueError`` on a non-zero status.
 """
 from __future__ import annotations
@@ -28,6 +27,7 @@ EXPORTS = [
     "spai_residual_pair_host", "spai_sample_step_dev", "spai_pack_taken_dev", "spai_reward_rows_dev", "spai_finalize_rewards_dev",
     "spai_ctx_enable_timing",
     "spai_ctx_last_timing", "spai_ctx_set_deletion_hint",
+    "spai_reward_batch_host_len", "spai_reward_batch_dev_len",
 ]
 
 
@@ -82,6 +82,8 @@ def load():
     lib.spai_ctx_set_workspace_limit.argtypes = [pv, i64]
     lib.spai_reward_batch_host.argtypes = [pv, pv, i64, i64, i64, dbl, i32, i32, pv, pv, pv, pv]
     lib.spai_reward_batch_dev.argtypes = [pv, pv, i64, i64, i64, dbl, i32, i32, pv, pv, pv, pv]
+    lib.spai_reward_batch_host_len.argtypes = [pv, pv, i32, pv, i64, i64, i64, dbl, i32, i32, pv, pv, pv, pv]
+    lib.spai_reward_batch_dev_len.argtypes = [pv, pv, i32, pv, i64, i64, i64, dbl, i32, i32, pv, pv, pv, pv]
     lib.spai_kept_mask_dev.argtypes = [pv, pv, i64, i64, i64, pv, pv]
     lib.spai_reward_from_taken_dev.argtypes = [pv, pv, i64, i64, dbl, i32, i32, pv, pv, pv, pv]
     lib.spai_row_index_sets.argtypes = [pv, i64, p64, pv, p64, pv]
@@ -97,7 +99,7 @@ def load():
     for name in EXPORTS:
         if name not in ("spai_last_error", "spai_ctx_destroy"):
             getattr(lib, name).restype = i32
-    if lib.spai_abi_version() != 1:
+    if lib.spai_abi_version() != 2:
         raise SpaiError(f"ABI mismatch: library reports {lib.spai_abi_version()}")
     _lib = lib
     return lib

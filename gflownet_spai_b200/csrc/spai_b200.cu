@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "k0_masks.cuh"
+#include "k0b_bucket.cuh"
 #include "k1_plan.cuh"
 #include "k2_ls.cuh"
 #include "k2g_gram.cuh"
@@ -893,8 +894,25 @@ struct spai_ctx {
   Workspace ws;
   PhaseTimer pt;
   spai_timing last = {};
-  int64_t row_lo = 0, row_hi = -1;      // row-range evaluation (spai_reward_rows_dev), reset after the call
-  bool partial_only = false;
+  // one-time table/plan builds are enqueued on the stream of the call that needs them first;
+  // `build_ev` orders every later call (any stream) after the last build
+  cudaEvent_t build_ev = nullptr;
+  bool build_pending = false;
+  int64_t build_bytes_seen = 0;
+  int wait_builds(cudaStream_t st) {
+    if (build_pending) SPAI_CUDA(cudaStreamWaitEvent(st, build_ev, 0));
+    return SPAI_OK;
+  }
+  int mark_builds(cudaStream_t st) {          // called after the ensure_* steps of a call
+    const int64_t now = plan_arena[0].bytes + plan_arena[1].bytes;
+    if (now != build_bytes_seen) {
+      if (!build_ev) SPAI_CUDA(cudaEventCreateWithFlags(&build_ev, cudaEventDisableTiming));
+      SPAI_CUDA(cudaEventRecord(build_ev, st));
+      build_pending = true;
+      build_bytes_seen = now;
+    }
+    return SPAI_OK;
+  }
 };
 
 namespace spai {
@@ -1231,6 +1249,7 @@ void spai_ctx_destroy(spai_ctx* c) {
   if (!c) return;
   DeviceGuard guard(c->device);
   c->pt.destroy();
+  if (c->build_ev) cudaEventDestroy(c->build_ev);
   delete c;
 }
 
@@ -1327,23 +1346,93 @@ struct RowTrimmer {          // worker threads publish lengths group by group
   ~RowTrimmer() { for (auto& t : workers) t.join(); }
 };
 
-// K0 for rows [0, bc) of `act` (device-accessible pointer, leading dimension act_ld):
-// shared-memory bitmask per trajectory when it fits, else init + global RED.
-static int launch_k0(const Pattern& P, const int64_t* act, int64_t bc, int64_t T, int64_t act_ld,
-                     uint32_t* mask, long long* nnz0, const int32_t* row_len, cudaStream_t st, int* launches,
-                     bool* nnz_fused) {
+// Scratch of the two-pass mask build (K0b, k0b_bucket.cuh) for one group of trajectories.
+struct K0bScratch {
+  uint16_t* stage = nullptr;     // [group][ld_stage] sorted 16-bit local ids
+  uint16_t* hdr = nullptr;       // [group][nchunks][C + 1]
+  int64_t group = 0, ld_stage = 0, nchunks = 0;
+  int C = 0;
+};
+static inline bool k0_fits_smem(int64_t W) { return W * 4 <= K0S_MAX_SMEM; }
+static inline int k0_variant() {             // A/B + test switch, read per call
+  const char* e = getenv("SPAI_K0_VARIANT");
+  return !e ? 0 : (!strcmp(e, "red") ? 1 : (!strcmp(e, "smem") ? 2 : (!strcmp(e, "bucket") ? 3 : 0)));
+}
+// K0b applies when the bitmask exceeds one CTA's shared memory and the segment count fits the sort kernel
+static inline bool k0b_applies(const Pattern& P, int64_t T) {
+  if (k0_variant() == 1 || T <= 0) return false;
+  const int64_t C = ceil_div(P.E, (int64_t)1 << K0B_SEG_SHIFT);
+  if (C > K0B_MAX_SEGS) return false;
+  return !k0_fits_smem(P.words()) || k0_variant() == 3;
+}
+// trajectories per sort+build launch pair: the staged ids of a group (2 bytes each) should stay in L2
+// between the two passes; SPAI_K0B_GROUP overrides (A/B)
+static int64_t k0b_group(int64_t bc, int64_t T, int64_t C) {
+  const char* e = getenv("SPAI_K0B_GROUP");
+  const int64_t forced = e ? atoll(e) : 0;
+  if (forced > 0) return std::min(bc, forced);
+  const int64_t tasks = ceil_div(C, (int64_t)K0B_R);
+  int64_t g = ((int64_t)96 << 20) / std::max<int64_t>(2 * T, 1);       // <= 96 MB of staged ids at full length
+  g = std::max(g, ceil_div((int64_t)2 * 148, tasks));                   // >= 2 build CTAs per SM
+  g = std::max<int64_t>(g, 8);
+  return std::min(bc, g);
+}
+static void k0b_plan(const Pattern& P, int64_t bc, int64_t T, K0bScratch* sc) {
+  sc->C = (int)ceil_div(P.E, (int64_t)1 << K0B_SEG_SHIFT);
+  sc->nchunks = ceil_div(T, (int64_t)K0B_CHUNK);
+  sc->ld_stage = sc->nchunks * K0B_CHUNK;
+  sc->group = k0b_group(bc, T, sc->C);
+}
+static int64_t k0b_bytes(const K0bScratch& sc) {
+  return padded(sc.group * sc.ld_stage * 2) + padded(sc.group * sc.nchunks * (sc.C + 1) * 2);
+}
+
+// K0 for rows [0, bc) of `act` (device-accessible pointer, ids of `elem` bytes, leading
+// dimension act_ld): shared-memory bitmask per trajectory when it fits, else the two-pass
+// segment build (K0b); init + global RED only for patterns beyond K0b's envelope.
+static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, int64_t T, int64_t act_ld,
+                     uint32_t* mask, long long* nnz0, const int32_t* row_len, const K0bScratch* sc,
+                     cudaStream_t st, int* launches, bool* nnz_fused) {
   const int64_t W = P.words();
-  static const int k0_variant = [] {
-    const char* v = getenv("SPAI_K0_VARIANT");
-    return !v ? 0 : (!strcmp(v, "red") ? 1 : (!strcmp(v, "smem") ? 2 : 0));
-  }();
-  const bool fits = W * 4 <= K0S_MAX_SMEM;
-  if (fits && k0_variant != 1 && T > 0) {
-    SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   K0S_MAX_SMEM));
-    k0_mask_build_smem_kernel<<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(
-        act, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, nnz0, row_len);
+  const int32_t* eslot = P.identity_perm ? nullptr : P.edge_slot;
+  const int64_t* a64 = reinterpret_cast<const int64_t*>(act);
+  const int32_t* a32 = reinterpret_cast<const int32_t*>(act);
+  if (k0_fits_smem(W) && k0_variant() != 1 && k0_variant() != 3 && T > 0) {
+    if (elem == 8) {
+      SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0S_MAX_SMEM));
+      k0_mask_build_smem_kernel<int64_t><<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(a64, bc, T, act_ld, eslot, P.E, mask, W, nnz0, row_len);
+    } else {
+      SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0S_MAX_SMEM));
+      k0_mask_build_smem_kernel<int32_t><<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(a32, bc, T, act_ld, eslot, P.E, mask, W, nnz0, row_len);
+    }
     SPAI_CUDA(cudaGetLastError()); ++*launches;
+    *nnz_fused = true;
+  } else if (sc && sc->stage && k0b_applies(P, T)) {
+    const int C = sc->C;
+    const size_t ssm = k0b_sort_smem(C);
+    const size_t bsm = (size_t)std::min<int64_t>((int64_t)K0B_R, C) * K0B_SEG_WORDS * 4;
+    const int tasks = (int)ceil_div(C, (int64_t)K0B_R);
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0b_sort_smem(K0B_MAX_SEGS)));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0b_sort_smem(K0B_MAX_SEGS)));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
+    SPAI_CUDA(cudaMemsetAsync(nnz0, 0, (size_t)bc * 8, st));
+    for (int64_t g0 = 0; g0 < bc; g0 += sc->group) {
+      const int64_t gb = std::min(sc->group, bc - g0);
+      const int64_t nblk = gb * sc->nchunks;
+      if (nblk >= ((int64_t)1 << 31) || gb * tasks >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
+      const int32_t* rl = row_len ? row_len + g0 : nullptr;
+      if (elem == 8)
+        k0b_sort_kernel<int64_t><<<(unsigned)nblk, K0B_THREADS, ssm, st>>>(a64 + g0 * act_ld, T, act_ld, rl, eslot, P.E, C,
+                                                                         sc->stage, sc->ld_stage, sc->hdr, sc->nchunks);
+      else
+        k0b_sort_kernel<int32_t><<<(unsigned)nblk, K0B_THREADS, ssm, st>>>(a32 + g0 * act_ld, T, act_ld, rl, eslot, P.E, C,
+                                                                         sc->stage, sc->ld_stage, sc->hdr, sc->nchunks);
+      SPAI_CUDA(cudaGetLastError()); ++*launches;
+      k0b_build_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
+          sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
+          reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks);
+      SPAI_CUDA(cudaGetLastError()); ++*launches;
+    }
     *nnz_fused = true;
   } else {
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
@@ -1354,8 +1443,10 @@ static int launch_k0(const Pattern& P, const int64_t* act, int64_t bc, int64_t T
       const int64_t chunks_t = ceil_div(T, 256 * U);
       const int64_t nblk = chunks_t * bc;
       if (nblk >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
-      k0_mask_clear_kernel<U><<<(unsigned)nblk, 256, 0, st>>>(
-          act, bc, T, act_ld, P.identity_perm ? nullptr : P.edge_slot, P.E, mask, W, chunks_t, row_len);
+      if (elem == 8)
+        k0_mask_clear_kernel<U, int64_t><<<(unsigned)nblk, 256, 0, st>>>(a64, bc, T, act_ld, eslot, P.E, mask, W, chunks_t, row_len);
+      else
+        k0_mask_clear_kernel<U, int32_t><<<(unsigned)nblk, 256, 0, st>>>(a32, bc, T, act_ld, eslot, P.E, mask, W, chunks_t, row_len);
       SPAI_CUDA(cudaGetLastError()); ++*launches;
     }
     *nnz_fused = false;
@@ -1365,42 +1456,82 @@ static int launch_k0(const Pattern& P, const int64_t* act, int64_t bc, int64_t T
 
 enum MaskSource { FROM_ACTIONS_DEV, FROM_ACTIONS_HOST, FROM_TAKEN_DEV };
 
-// Shared driver of the three reward entry points: chunk the batch so the scratch
+// One reward call. Everything a call depends on travels here (nothing per-call is
+// kept in the context, so a context can serve calls with different parameters back to back).
+struct RewardCall {
+  MaskSource src = FROM_ACTIONS_DEV;
+  const void* input = nullptr;          // actions (elem bytes per id) or taken bitmask
+  int elem = 8;                         // 8: int64 ids (the reference's format), 4: int32 ids
+  const int32_t* row_len = nullptr;     // optional valid length of every row (host array for the host entry,
+                                        // device array for the device entry); entries beyond it are not read
+  int64_t B = 0, T = 0, ld = 0;
+  double alpha = 0.5;
+  int mode = SPAI_MODE_COPY, dtype = SPAI_F32;
+  double* reward = nullptr; double* residual = nullptr; int64_t* nnz_m = nullptr;
+  bool out_host = false;
+  uint8_t* kept_bytes_dev = nullptr;    // mask-only call (spai_kept_mask_dev)
+  int64_t row_lo = 0, row_hi = -1;      // row-range evaluation (spai_reward_rows_dev)
+  bool partial_only = false;
+  int64_t t_hint = 0;                   // longest trajectory (0 = unknown); selects a kernel only
+  void* stream = nullptr;
+};
+
+// Shared driver of the reward entry points: chunk the batch so the scratch
 // stays under the workspace limit, build slot-order masks, evaluate.
-static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t B, int64_t T, int64_t ld,
-                         double alpha, int mode, int dtype, double* reward, double* residual,
-                         int64_t* nnz_m, bool out_host, uint8_t* kept_bytes_dev, void* stream) {
-  if (!c || B < 0 || (B && !input && (src == FROM_TAKEN_DEV || T > 0)) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS && mode != SPAI_MODE_LS_GRAM) ||
-      (dtype != SPAI_F32 && dtype != SPAI_F64) || (src != FROM_TAKEN_DEV && (T < 0 || ld < T))) {
+static int reward_driver(spai_ctx* c, const RewardCall& rc) {
+  const MaskSource src = rc.src;
+  const int64_t B = rc.B, T = rc.T, ld = rc.ld;
+  const int mode = rc.mode, dtype = rc.dtype;
+  if (!c || B < 0 || (B && !rc.input && (src == FROM_TAKEN_DEV || T > 0)) || (mode != SPAI_MODE_COPY && mode != SPAI_MODE_LS && mode != SPAI_MODE_LS_GRAM) ||
+      (dtype != SPAI_F32 && dtype != SPAI_F64) || (src != FROM_TAKEN_DEV && (T < 0 || ld < T)) || (rc.elem != 8 && rc.elem != 4)) {
     set_error("reward: invalid arguments");
     return SPAI_ERR_INVALID;
   }
   if (B == 0) return SPAI_OK;
   DeviceGuard guard(c->device);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool mask_only = kept_bytes_dev != nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(rc.stream);
+  const bool mask_only = rc.kept_bytes_dev != nullptr;
+  const bool out_host = rc.out_host;
+  const int64_t esz = rc.elem;
+  // one-time builds are enqueued on the stream of the call that triggers them; later calls on
+  // other streams wait for the recorded event before they read the tables
+  SPAI_TRY(c->wait_builds(st));
   if (!mask_only) SPAI_TRY(ensure_plan(c, dtype, mode != SPAI_MODE_COPY, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM) SPAI_TRY(ensure_gram(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_LS_GRAM && B >= 64) SPAI_TRY(ensure_lut_ls(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_LS && B >= 64) SPAI_TRY(ensure_lut_qr(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_COPY && B >= 64) SPAI_TRY(ensure_lut(c, dtype, st));
   if (!mask_only) c->plan[dtype].tables_on = B >= 64;
-  const int64_t t_len = (src == FROM_TAKEN_DEV) ? c->deletion_hint : T;     // longest trajectory (0 = unknown)
+  int64_t t_len = rc.t_hint;                                   // longest trajectory (0 = unknown)
+  if (src != FROM_TAKEN_DEV) {
+    t_len = T;
+    if (rc.row_len && src == FROM_ACTIONS_HOST) {              // host lengths are free to inspect
+      int64_t m = 0;
+      for (int64_t b = 0; b < B; ++b) {
+        if (rc.row_len[b] < 0) { set_error("reward: negative row length"); return SPAI_ERR_INVALID; }
+        m = std::max<int64_t>(m, std::min<int64_t>(rc.row_len[b], T));
+      }
+      t_len = m;
+    }
+  }
   {
     const char* force = getenv("SPAI_K3_SPARSE");
     const bool want = force ? atoi(force) != 0 : (t_len > 0 && t_len * K3S_MIN_RATIO <= c->P.E);
     if (!mask_only && mode == SPAI_MODE_COPY && want) SPAI_TRY(ensure_sparse(c, dtype, st));
   }
+  SPAI_TRY(c->mark_builds(st));
   const Plan& plan = c->plan[mask_only ? SPAI_F32 : dtype];
   const Pattern& P = c->P;
   const int64_t W = P.words();
+  const bool use_k0b = src != FROM_TAKEN_DEV && k0b_applies(P, T);
 
   // chunk size
   int64_t Bc = B;
   auto need_for = [&](int64_t bc) {
     const int64_t bp = round_up(bc, 32);
     int64_t need = padded(bc * std::max<int64_t>(W, 1) * 4) + padded(bp * 8);   // mask + fused popcount
-    if (src == FROM_ACTIONS_HOST) need += padded(bc * std::max<int64_t>(T, 1) * 8) + padded(bc * 4);
+    if (src == FROM_ACTIONS_HOST) need += padded(bc * std::max<int64_t>(T, 1) * esz) + padded(bc * 4);
+    if (use_k0b) { K0bScratch sc; k0b_plan(P, bc, T, &sc); need += k0b_bytes(sc); }
     if (out_host) need += 3 * padded(bp * 8);
     if (!mask_only) need += eval_bytes(plan, plan_shape(plan, mode, dtype, bc, c->sm_count), W, dtype);
     return need;
@@ -1421,90 +1552,108 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     const int64_t bp = round_up(bc, 32);
     Carver cv{reinterpret_cast<char*>(c->ws.base), reinterpret_cast<char*>(c->ws.base) + c->ws.bytes};
     uint32_t* mask = cv.take<uint32_t>(bc * std::max<int64_t>(W, 1));
-    const int64_t* act_dev = nullptr;
+    const char* act_dev = nullptr;
     int64_t act_ld = ld;
     const int32_t* row_len_dev = nullptr;
     long long* nnz0 = cv.take<long long>(bp);
     const long long* nnz_ready = nullptr;
     bool k0_done = false;
+    K0bScratch sc;
+    if (use_k0b) {
+      k0b_plan(P, bc, T, &sc);
+      sc.stage = cv.take<uint16_t>(sc.group * sc.ld_stage);
+      sc.hdr = cv.take<uint16_t>(sc.group * sc.nchunks * (sc.C + 1));
+    }
     if (src == FROM_ACTIONS_HOST) {
-      int64_t* buf = cv.take<int64_t>(bc * std::max<int64_t>(T, 1));
+      char* buf = cv.take<char>(bc * std::max<int64_t>(T, 1) * esz);
       int32_t* len_dev = cv.take<int32_t>(bc);
-      const int64_t* hbase = reinterpret_cast<const int64_t*>(input) + b0 * ld;
+      const char* hbase = reinterpret_cast<const char*>(rc.input) + b0 * ld * esz;
       act_ld = T;
-      if (T >= 4096) {
-        // workers trim rows (scan back over the -1 padding) while this thread feeds the GPU
-        if (!trimmer || trimmer_b0 != b0) { trimmer.reset(new RowTrimmer(hbase, bc, T, ld)); trimmer_b0 = b0; }
+      if (T >= 4096 || rc.row_len) {
+        // valid length of every row: the caller's (no host pass over the data at all), else worker
+        // threads scan each row back over its -1 padding while this thread feeds the GPU
+        const int32_t* hlen = rc.row_len ? rc.row_len + b0 : nullptr;
+        if (!hlen && (!trimmer || trimmer_b0 != b0)) {
+          if (esz != 8) { set_error("reward: int32 host actions need row lengths"); return SPAI_ERR_INVALID; }
+          trimmer.reset(new RowTrimmer(reinterpret_cast<const int64_t*>(hbase), bc, T, ld));
+          trimmer_b0 = b0;
+        }
+        auto len_of = [&](int64_t b) -> int64_t { return hlen ? std::min<int64_t>(hlen[b], T) : trimmer->len[b]; };
         // zero-copy: pinned host memory is device-accessible (UVA), so K0 can stream the valid
         // prefix of every row straight over PCIe into its shared-memory bitmask — no staging
         // buffer and no per-row copy call. Pageable input falls back to per-row cudaMemcpyAsync.
-        const int64_t* hdev = nullptr;
+        const char* hdev = nullptr;
         static const bool force_memcpy = [] { const char* v = getenv("SPAI_H2D"); return v && !strcmp(v, "memcpy"); }();
         if (!force_memcpy && W > 0) {
           cudaPointerAttributes at;
           if (cudaPointerGetAttributes(&at, hbase) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-            hdev = reinterpret_cast<const int64_t*>(at.devicePointer);
+            hdev = reinterpret_cast<const char*>(at.devicePointer);
           else
             cudaGetLastError();
         }
         if (hdev) {
-          constexpr int64_t SG = 256;                                  // rows per K0 launch
+          // with caller lengths one launch covers the chunk; with the trimmer K0 follows the workers
+          const int64_t SG = hlen ? bc : 256;                          // rows per K0 launch
           if (pt->on) cudaEventRecord(pt->ev[0], st);
+          if (hlen) SPAI_CUDA(cudaMemcpyAsync(len_dev, hlen, (size_t)bc * 4, cudaMemcpyHostToDevice, st));
           for (int64_t sg = 0; sg < bc; sg += SG) {
             const int64_t nr = std::min(SG, bc - sg);
-            for (int64_t g = sg / RowTrimmer::GROUP; g * RowTrimmer::GROUP < sg + nr; ++g) trimmer->wait(g);
-            SPAI_CUDA(cudaMemcpyAsync(len_dev + sg, trimmer->len.data() + sg, (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+            if (!hlen) {
+              for (int64_t g = sg / RowTrimmer::GROUP; g * RowTrimmer::GROUP < sg + nr; ++g) trimmer->wait(g);
+              SPAI_CUDA(cudaMemcpyAsync(len_dev + sg, trimmer->len.data() + sg, (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+            }
             bool fused = false;
-            SPAI_TRY(launch_k0(P, hdev + sg * ld, nr, T, ld, mask + sg * W, nnz0 + sg, len_dev + sg, st, &launches,
-                               &fused));
+            SPAI_TRY(launch_k0(P, hdev + sg * ld * esz, (int)esz, nr, T, ld, mask + sg * W, nnz0 + sg, len_dev + sg,
+                               use_k0b ? &sc : nullptr, st, &launches, &fused));
             if (fused) nnz_ready = nnz0;
           }
           k0_done = true;
         } else {
-          for (int64_t g = 0; g * RowTrimmer::GROUP < bc; ++g) {
-            trimmer->wait(g);
-            const int64_t hi = std::min(bc, (g + 1) * RowTrimmer::GROUP);
-            for (int64_t b = g * RowTrimmer::GROUP; b < hi; ++b) {
-              const int64_t n = trimmer->len[b];
-              if (n) SPAI_CUDA(cudaMemcpyAsync(buf + b * T, hbase + b * ld, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-            }
+          // staged: per-row prefix copies (pageable memory)
+          for (int64_t b = 0; b < bc; ++b) {
+            if (!hlen && b % RowTrimmer::GROUP == 0) trimmer->wait(b / RowTrimmer::GROUP);
+            const int64_t n = len_of(b);
+            if (n) SPAI_CUDA(cudaMemcpyAsync(buf + b * T * esz, hbase + b * ld * esz, (size_t)n * esz, cudaMemcpyHostToDevice, st));
           }
-          SPAI_CUDA(cudaMemcpyAsync(len_dev, trimmer->len.data(), (size_t)bc * 4, cudaMemcpyHostToDevice, st));
+          if (hlen) SPAI_CUDA(cudaMemcpyAsync(len_dev, hlen, (size_t)bc * 4, cudaMemcpyHostToDevice, st));
+          else SPAI_CUDA(cudaMemcpyAsync(len_dev, trimmer->len.data(), (size_t)bc * 4, cudaMemcpyHostToDevice, st));
         }
         row_len_dev = len_dev;
         h2d_bytes += (double)bc * 4;
-        for (int64_t b = 0; b < bc; ++b) h2d_bytes += 8.0 * trimmer->len[b];
+        for (int64_t b = 0; b < bc; ++b) h2d_bytes += (double)esz * len_of(b);
       } else if (ld == T) {
-        SPAI_CUDA(cudaMemcpyAsync(buf, hbase, (size_t)bc * T * 8, cudaMemcpyHostToDevice, st));
-        h2d_bytes += (double)bc * T * 8;
+        SPAI_CUDA(cudaMemcpyAsync(buf, hbase, (size_t)bc * T * esz, cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double)bc * T * esz;
       } else {
-        SPAI_CUDA(cudaMemcpy2DAsync(buf, (size_t)T * 8, hbase, (size_t)ld * 8, (size_t)T * 8, (size_t)bc,
+        SPAI_CUDA(cudaMemcpy2DAsync(buf, (size_t)T * esz, hbase, (size_t)ld * esz, (size_t)T * esz, (size_t)bc,
                                     cudaMemcpyHostToDevice, st));
-        h2d_bytes += (double)bc * T * 8;
+        h2d_bytes += (double)bc * T * esz;
       }
       act_dev = buf;
     } else if (src == FROM_ACTIONS_DEV) {
-      act_dev = reinterpret_cast<const int64_t*>(input) + b0 * ld;
+      act_dev = reinterpret_cast<const char*>(rc.input) + b0 * ld * esz;
+      row_len_dev = rc.row_len ? rc.row_len + b0 : nullptr;
     }
     double* o_rw = nullptr; double* o_rs = nullptr; int64_t* o_nz = nullptr;
     if (out_host) {
       o_rw = cv.take<double>(bp); o_rs = cv.take<double>(bp); o_nz = cv.take<int64_t>(bp);
     } else {
-      o_rw = reward ? reward + b0 : nullptr; o_rs = residual ? residual + b0 : nullptr;
-      o_nz = nnz_m ? nnz_m + b0 : nullptr;
+      o_rw = rc.reward ? rc.reward + b0 : nullptr; o_rs = rc.residual ? rc.residual + b0 : nullptr;
+      o_nz = rc.nnz_m ? rc.nnz_m + b0 : nullptr;
     }
     if (pt->on && !k0_done) cudaEventRecord(pt->ev[0], st);
     if (W > 0) {
       if (src == FROM_TAKEN_DEV) {
         const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(W * bc, 256), 148 * 32);
         k0_mask_from_taken_kernel<<<blocks, 256, 0, st>>>(
-            reinterpret_cast<const uint32_t*>(input) + b0 * ld, ld, P.identity_perm ? nullptr : P.slot_edge,
+            reinterpret_cast<const uint32_t*>(rc.input) + b0 * ld, ld, P.identity_perm ? nullptr : P.slot_edge,
             P.E, mask, W, bc);
         SPAI_CUDA(cudaGetLastError()); ++launches;
       } else {
         if (!k0_done) {
           bool fused = false;
-          SPAI_TRY(launch_k0(P, act_dev, bc, T, act_ld, mask, nnz0, row_len_dev, st, &launches, &fused));
+          SPAI_TRY(launch_k0(P, act_dev, (int)esz, bc, T, act_ld, mask, nnz0, row_len_dev, use_k0b ? &sc : nullptr, st,
+                             &launches, &fused));
           if (fused) nnz_ready = nnz0;
         }
       }
@@ -1514,7 +1663,7 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
       if (P.E > 0) {
         const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(P.E * bc, 256), 148 * 32);
         k0_kept_bytes_kernel<<<blocks, 256, 0, st>>>(mask, W, bc, P.identity_perm ? nullptr : P.edge_slot, P.E,
-                                                    kept_bytes_dev + b0 * P.E);
+                                                    rc.kept_bytes_dev + b0 * P.E);
         SPAI_CUDA(cudaGetLastError()); ++launches;
       }
       ++chunks;
@@ -1523,13 +1672,13 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
     char* scratch = cv.take<char>(0);
     const int64_t left = (reinterpret_cast<char*>(c->ws.base) + c->ws.bytes) - scratch;
     SPAI_TRY(eval_masks(P, plan, mode, dtype, mask, bc, scratch, left, c->sm_count, (double)c->n, res0,
-                        (double)c->flops0, alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready, c->row_lo,
-                        c->row_hi, c->partial_only, t_len));
+                        (double)c->flops0, rc.alpha, o_rw, o_rs, o_nz, st, pt, &launches, nnz_ready, rc.row_lo,
+                        rc.row_hi, rc.partial_only, t_len));
     if (pt->on) cudaEventRecord(pt->ev[4], st);
     if (out_host) {
-      if (reward) SPAI_CUDA(cudaMemcpyAsync(reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
-      if (residual) SPAI_CUDA(cudaMemcpyAsync(residual + b0, o_rs, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
-      if (nnz_m) SPAI_CUDA(cudaMemcpyAsync(nnz_m + b0, o_nz, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+      if (rc.reward) SPAI_CUDA(cudaMemcpyAsync(rc.reward + b0, o_rw, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+      if (rc.residual) SPAI_CUDA(cudaMemcpyAsync(rc.residual + b0, o_rs, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
+      if (rc.nnz_m) SPAI_CUDA(cudaMemcpyAsync(rc.nnz_m + b0, o_nz, (size_t)bc * 8, cudaMemcpyDeviceToHost, st));
     }
     ++chunks;
     if (pt->on) {
@@ -1553,6 +1702,17 @@ static int reward_driver(spai_ctx* c, MaskSource src, const void* input, int64_t
   return SPAI_OK;
 }
 
+// host entry points must not return while kernels may still read the caller's pinned buffer
+static int reward_driver_host(spai_ctx* c, const RewardCall& rc) {
+  const int s = reward_driver(c, rc);
+  if (s != SPAI_OK && c) {
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(rc.stream));
+    cudaGetLastError();
+  }
+  return s;
+}
+
 }  // namespace spai
 
 extern "C" {
@@ -1560,30 +1720,62 @@ extern "C" {
 int spai_reward_batch_host(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
                            double alpha, int mode, int dtype, double* reward, double* residual,
                            int64_t* nnz_m, void* stream) {
-  return reward_driver(c, FROM_ACTIONS_HOST, actions, B, T, ld, alpha, mode, dtype, reward, residual, nnz_m,
-                       true, nullptr, stream);
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_HOST; rc.input = actions; rc.B = B; rc.T = T; rc.ld = ld; rc.alpha = alpha;
+  rc.mode = mode; rc.dtype = dtype; rc.reward = reward; rc.residual = residual; rc.nnz_m = nnz_m;
+  rc.out_host = true; rc.stream = stream;
+  return reward_driver_host(c, rc);
 }
 
 int spai_reward_batch_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
                           double alpha, int mode, int dtype, double* reward, double* residual,
                           int64_t* nnz_m, void* stream) {
-  return reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, alpha, mode, dtype, reward, residual, nnz_m,
-                       false, nullptr, stream);
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_DEV; rc.input = actions; rc.B = B; rc.T = T; rc.ld = ld; rc.alpha = alpha;
+  rc.mode = mode; rc.dtype = dtype; rc.reward = reward; rc.residual = residual; rc.nnz_m = nnz_m;
+  rc.stream = stream;
+  return reward_driver(c, rc);
+}
+
+int spai_reward_batch_host_len(spai_ctx* c, const void* actions, int id_bytes, const int32_t* row_len,
+                               int64_t B, int64_t T, int64_t ld, double alpha, int mode, int dtype,
+                               double* reward, double* residual, int64_t* nnz_m, void* stream) {
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_HOST; rc.input = actions; rc.elem = id_bytes; rc.row_len = row_len;
+  rc.B = B; rc.T = T; rc.ld = ld; rc.alpha = alpha; rc.mode = mode; rc.dtype = dtype;
+  rc.reward = reward; rc.residual = residual; rc.nnz_m = nnz_m; rc.out_host = true; rc.stream = stream;
+  return reward_driver_host(c, rc);
+}
+
+int spai_reward_batch_dev_len(spai_ctx* c, const void* actions, int id_bytes, const int32_t* row_len,
+                              int64_t B, int64_t T, int64_t ld, double alpha, int mode, int dtype,
+                              double* reward, double* residual, int64_t* nnz_m, void* stream) {
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_DEV; rc.input = actions; rc.elem = id_bytes; rc.row_len = row_len;
+  rc.B = B; rc.T = T; rc.ld = ld; rc.alpha = alpha; rc.mode = mode; rc.dtype = dtype;
+  rc.reward = reward; rc.residual = residual; rc.nnz_m = nnz_m; rc.stream = stream;
+  return reward_driver(c, rc);
 }
 
 int spai_reward_from_taken_dev(spai_ctx* c, const uint32_t* taken, int64_t B, int64_t words_ld,
                                double alpha, int mode, int dtype, double* reward, double* residual,
                                int64_t* nnz_m, void* stream) {
   if (c && words_ld < c->P.words()) { set_error("taken mask has %lld words per sample, need >= %lld", (long long)words_ld, (long long)c->P.words()); return SPAI_ERR_INVALID; }
-  return reward_driver(c, FROM_TAKEN_DEV, taken, B, 0, words_ld, alpha, mode, dtype, reward, residual, nnz_m,
-                       false, nullptr, stream);
+  RewardCall rc;
+  rc.src = FROM_TAKEN_DEV; rc.input = taken; rc.B = B; rc.T = 0; rc.ld = words_ld; rc.alpha = alpha;
+  rc.mode = mode; rc.dtype = dtype; rc.reward = reward; rc.residual = residual; rc.nnz_m = nnz_m;
+  rc.stream = stream;
+  if (c) { rc.t_hint = c->deletion_hint; c->deletion_hint = 0; }      // the hint serves ONE call (no stale hints)
+  return reward_driver(c, rc);
 }
 
 int spai_kept_mask_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t T, int64_t ld,
                        uint8_t* out, void* stream) {
   if (!out) return SPAI_ERR_INVALID;
-  return reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, 0.5, SPAI_MODE_COPY, SPAI_F32, nullptr, nullptr,
-                       nullptr, false, out, stream);
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_DEV; rc.input = actions; rc.B = B; rc.T = T; rc.ld = ld;
+  rc.kept_bytes_dev = out; rc.stream = stream;
+  return reward_driver(c, rc);
 }
 
 int spai_row_index_sets(spai_ctx* c, int64_t row, int64_t* num_j, int64_t* j_host, int64_t* num_i,
@@ -1706,11 +1898,11 @@ int spai_reward_rows_dev(spai_ctx* c, const int64_t* actions, int64_t B, int64_t
     set_error("spai_reward_rows_dev: invalid arguments");
     return SPAI_ERR_INVALID;
   }
-  c->row_lo = row_begin; c->row_hi = row_end; c->partial_only = true;
-  const int st = reward_driver(c, FROM_ACTIONS_DEV, actions, B, T, ld, 0.5, mode, dtype, nullptr, res2_partial,
-                               nnz_m, false, nullptr, stream);
-  c->row_lo = 0; c->row_hi = -1; c->partial_only = false;
-  return st;
+  RewardCall rc;
+  rc.src = FROM_ACTIONS_DEV; rc.input = actions; rc.B = B; rc.T = T; rc.ld = ld; rc.mode = mode; rc.dtype = dtype;
+  rc.residual = res2_partial; rc.nnz_m = nnz_m; rc.row_lo = row_begin; rc.row_hi = row_end; rc.partial_only = true;
+  rc.stream = stream;
+  return reward_driver(c, rc);
 }
 
 int spai_finalize_rewards_dev(spai_ctx* c, const double* res2, const int64_t* nnz_m, int64_t B, double alpha,

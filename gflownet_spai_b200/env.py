@@ -137,11 +137,14 @@ class SpaiContext:
 
     # ------------------------------------------------------------------ reward
     def reward_batch(self, actions: torch.Tensor, alpha: float, mode: str = "copy",
-                     dtype: torch.dtype = torch.float32, want=("reward", "residual", "nnz_m")):
-        """actions int64[B, T] (CPU -> host entry point with copies inside; CUDA ->
-        device entry point). Returns dict of tensors on the same side as `actions`."""
-        if actions.dtype != torch.int64 or actions.dim() != 2:
-            raise ValueError("actions must be an int64 [B, T] tensor")
+                     dtype: torch.dtype = torch.float32, want=("reward", "residual", "nnz_m"),
+                     lengths: torch.Tensor | None = None):
+        """actions int64 (or int32) [B, T] (CPU -> host entry point with copies inside; CUDA ->
+        device entry point). `lengths` (optional int32[B], same side as `actions`): valid length
+        of every row; entries beyond it are padding the caller vouches for and are never read
+        (spai_reward_batch_*_len). Returns dict of tensors on the same side as `actions`."""
+        if actions.dtype not in (torch.int64, torch.int32) or actions.dim() != 2:
+            raise ValueError("actions must be an int64 (or int32) [B, T] tensor")
         if actions.stride(1) != 1 and actions.shape[1] > 1:
             actions = actions.contiguous()
         b, t = actions.shape
@@ -153,15 +156,27 @@ class SpaiContext:
         dt = F32 if dtype == torch.float32 else F64
         on_dev = actions.is_cuda
         dev = actions.device if on_dev else torch.device("cpu")
+        if on_dev and actions.device.index != self.device:
+            raise ValueError("actions live on a different CUDA device than the context")
+        if lengths is not None:
+            if lengths.dtype != torch.int32 or lengths.numel() != b or lengths.device != actions.device:
+                raise ValueError("lengths must be an int32 [B] tensor on the same device as actions")
+            lengths = lengths.contiguous()
+        elif actions.dtype == torch.int32 and not on_dev:
+            raise ValueError("int32 host actions need lengths")
         out = {}
         out["reward"] = torch.empty(b, dtype=torch.float64, device=dev) if "reward" in want else None
         out["residual"] = torch.empty(b, dtype=torch.float64, device=dev) if "residual" in want else None
         out["nnz_m"] = torch.empty(b, dtype=torch.int64, device=dev) if "nnz_m" in want else None
-        fn = self._lib.spai_reward_batch_dev if on_dev else self._lib.spai_reward_batch_host
-        if on_dev and actions.device.index != self.device:
-            raise ValueError("actions live on a different CUDA device than the context")
-        check(fn(self._h, _ptr(actions), b, t, ld, float(alpha), md, dt, _ptr(out["reward"]),
-                 _ptr(out["residual"]), _ptr(out["nnz_m"]), self._stream()), "spai_reward_batch")
+        if lengths is None and actions.dtype == torch.int64:
+            fn = self._lib.spai_reward_batch_dev if on_dev else self._lib.spai_reward_batch_host
+            st = fn(self._h, _ptr(actions), b, t, ld, float(alpha), md, dt, _ptr(out["reward"]),
+                    _ptr(out["residual"]), _ptr(out["nnz_m"]), self._stream())
+        else:
+            fn = self._lib.spai_reward_batch_dev_len if on_dev else self._lib.spai_reward_batch_host_len
+            st = fn(self._h, _ptr(actions), actions.element_size(), _ptr(lengths), b, t, ld, float(alpha), md, dt,
+                    _ptr(out["reward"]), _ptr(out["residual"]), _ptr(out["nnz_m"]), self._stream())
+        check(st, "spai_reward_batch")
         return {k: v for k, v in out.items() if v is not None}
 
     def reward_rows(self, actions: torch.Tensor, row_begin: int, row_end: int, mode: str = "copy",
@@ -317,16 +332,19 @@ class PreconditionerEnv(Env):
         a = self.alpha if self.alpha is not None else alpha
         return float(a.detach()) if isinstance(a, torch.Tensor) else float(a)
 
-    def update_tensor(self, actions, alpha, want=("reward", "residual", "nnz_m")):
-        """Batch reward as tensors (no per-trajectory Python objects)."""
+    def update_tensor(self, actions, alpha, want=("reward", "residual", "nnz_m"), lengths=None):
+        """Batch reward as tensors (no per-trajectory Python objects). `lengths` (optional
+        int32[B]): valid length of every row, as the sampler's Log knows it (log.py:84-87);
+        the -1 padding behind it is then never read by host or device."""
         if not isinstance(actions, torch.Tensor):
             rows = [list(map(int, r)) for r in actions]
             t = max((len(r) for r in rows), default=0)
             actions = torch.tensor([r + [-1] * (t - len(r)) for r in rows], dtype=torch.int64).reshape(len(rows), t)
         if actions.dim() == 1:
             actions = actions.unsqueeze(0)
-        actions = actions.to(torch.int64)
-        return self.ctx.reward_batch(actions, self._alpha(alpha), self.mode, self.dtype, want)
+        if actions.dtype != torch.int32:
+            actions = actions.to(torch.int64)
+        return self.ctx.reward_batch(actions, self._alpha(alpha), self.mode, self.dtype, want, lengths=lengths)
 
     def update_from_taken(self, taken: torch.Tensor, alpha, max_deletions: int = 0):
         """Batch reward straight from the sampler's device-resident taken-bitmask

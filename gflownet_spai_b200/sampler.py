@@ -178,14 +178,27 @@ class GFlowNet(nn.Module):
 
     # ------------------------------------------------------------------ device sampler
     @staticmethod
-    def chosen_probs(p: torch.Tensor, actions_bt: torch.Tensor) -> torch.Tensor:
+    def chosen_probs(p: torch.Tensor, actions_bt: torch.Tensor, rest: torch.Tensor | None = None) -> torch.Tensor:
         """Differentiable probabilities of the drawn actions: p[a_t] divided by the
-        mass not yet taken before step t; 1.0 where the action is -1."""
+        mass not yet taken before step t (what the reference's per-step masked softmax
+        returns, policy.py:64-73); 1.0 where the action is -1.
+
+        The remaining mass is built WITHOUT cancellation: (mass of the ids the trajectory
+        never takes) + (suffix sum of the drawn ids' masses from step t on). `1 - cumsum`
+        loses every digit on long trajectories because an fp32 softmax sums to 1 only to
+        ~1e-6; here the denominator is >= p[a_t] by construction, so the result is in (0, 1]
+        for any policy. `rest` (optional, f64[B]) is the never-taken mass when the caller has
+        it exactly (GFlowNet.untaken_mass over the taken-bitmask); otherwise it is
+        sum(p) - sum(drawn), clamped at 0 (exact to 1e-16 * sum(p))."""
         valid = actions_bt >= 0
         idx = actions_bt.clamp(min=0)
-        pa = p.to(torch.float64)[idx] * valid
-        before = torch.cumsum(pa, dim=1) - pa
-        out = pa / (1.0 - before).clamp_min(1e-300)
+        p64 = p.to(torch.float64)
+        pa = p64[idx] * valid
+        if rest is None:
+            rest = (p64.sum() - pa.sum(dim=1)).clamp_min(0.0)
+        suffix = torch.flip(torch.cumsum(torch.flip(pa, dims=[1]), dim=1), dims=[1])
+        den = rest.to(pa.device)[:, None] + suffix
+        out = pa / torch.where(valid, den, torch.ones_like(den)).clamp_min(1e-300)
         return torch.where(valid, out, torch.ones_like(out)).to(p.dtype)
 
     def _sample_gumbel(self, logits, bsz, dev, generator, chunk_bytes=2 << 30):
@@ -250,6 +263,8 @@ class GFlowNet(nn.Module):
             return log if return_log else None
         if method != "step":
             raise ValueError("method must be 'step' or 'gumbel'")
+        if not bool(torch.isfinite(logits).all()):
+            raise RuntimeError("sample_states: the forward policy returned non-finite probabilities")
         acts, probs = [], []
         step = 0
         while True:
@@ -260,9 +275,11 @@ class GFlowNet(nn.Module):
             acts.append(act)
             probs.append(pr)
             step += 1
-            if step % self.check_every == 0 or step > a:
+            if step % self.check_every == 0 or step >= a:
                 if bool(done.all()):
                     break
+                if step >= a + 1:       # every id incl. the terminal has been offered: cannot happen with finite logits
+                    raise RuntimeError(f"sample_states: {int((done == 0).sum())} samples not finished after {step} steps")
         actions_tb = torch.stack(acts, dim=0)                     # [T', B]
         live = (actions_tb >= 0).any(dim=1)
         t_len = int(live.sum())                                   # drop all-finished trailing steps

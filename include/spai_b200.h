@@ -15,7 +15,10 @@
  *   - pointers named *_dev are device pointers on the context's device,
  *     *_host are host pointers (pinned host memory makes copies asynchronous);
  *   - calls enqueue on `stream`; only functions that fill HOST outputs
- *     synchronise that stream before returning.
+ *     synchronise that stream before returning (host entry points also synchronise
+ *     it before returning an error, so the caller's buffers are never read afterwards);
+ *   - one thread per context at a time; calls on different streams are ordered after the
+ *     context's one-time table builds by an internal event.
  */
 #ifndef SPAI_B200_H_
 #define SPAI_B200_H_
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPAI_ABI_VERSION 1
+#define SPAI_ABI_VERSION 2
 
 enum spai_status {
   SPAI_OK = 0,
@@ -105,7 +108,8 @@ int spai_ctx_set_workspace_limit(spai_ctx* ctx, int64_t bytes);
 /* Upper bound on the number of edges one trajectory removes, for the entry point that
  * carries no action list (spai_reward_from_taken_dev): lets the library pick the
  * deletion-driven kernel for short trajectories. 0 (default) = unknown. The bound only
- * selects a kernel; results do not depend on it. */
+ * selects a kernel; results do not depend on it. It applies to the NEXT
+ * spai_reward_from_taken_dev call only and is cleared by it (no stale hints). */
 int spai_ctx_set_deletion_hint(spai_ctx* ctx, int64_t max_deletions);
 
 /* PreconditionerEnv.update (preconditioner.py:32-52) for a whole batch:
@@ -124,6 +128,28 @@ int spai_reward_batch_dev(spai_ctx* ctx, const int64_t* actions_dev, int64_t B, 
                           int64_t ld, double alpha, int mode, int dtype,
                           double* reward_dev, double* residual_dev, int64_t* nnz_m_dev,
                           void* stream);
+
+/* The same update (preconditioner.py:32-52) for callers that KNOW the valid length of
+ * every row — the reference's Log does: a sample stops being logged once `done`
+ * (gflownet/log.py:84-87), so row b of `complete_actions` (gflownet.py:181) holds
+ * row_len[b] ids followed by -1 padding only.
+ *   actions   ids of `id_bytes` bytes each: 8 = int64 (the reference's tensor), 4 = int32
+ *             (device-resident samplers; halves the bytes the mask kernels stream);
+ *   row_len   i32[B], may be NULL (= T for every row). Entries at positions >= row_len[b] are
+ *             NOT read: the caller vouches that they are padding. With it no thread, host or
+ *             device, ever touches the padding (49 % of the cfg2 batch), and the host entry
+ *             needs no scan of the input at all.
+ *             _host_len: row_len is a HOST array; _dev_len: a DEVICE array.
+ * Ids inside the valid prefix keep the exact semantics of the plain entry points (-1 and ids
+ * outside [0, E) match no edge, duplicates collapse). int32 host actions require row_len. */
+int spai_reward_batch_host_len(spai_ctx* ctx, const void* actions_host, int id_bytes,
+                               const int32_t* row_len_host, int64_t B, int64_t T, int64_t ld,
+                               double alpha, int mode, int dtype, double* reward_host,
+                               double* residual_host, int64_t* nnz_m_host, void* stream);
+int spai_reward_batch_dev_len(spai_ctx* ctx, const void* actions_dev, int id_bytes,
+                              const int32_t* row_len_dev, int64_t B, int64_t T, int64_t ld,
+                              double alpha, int mode, int dtype, double* reward_dev,
+                              double* residual_dev, int64_t* nnz_m_dev, void* stream);
 
 /* gflownet/utils.py:315-323 on its own: kept-edge mask of every trajectory in
  * EDGE (caller) order, one byte per edge: out_dev u8[B, E]. The bit-exact

@@ -1,6 +1,8 @@
 """Import the live reference (read-only checkout) as an oracle — TEST
-INFRASTRUCTURE. Works only where ``/root/reference`` exists (the build
-container); nothing on the GPU box may rely on it.
+INFRASTRUCTURE. Uses ``/root/reference`` in the build container; on the GPU box
+(where that path does not exist) the unmodified copy staged under ``baseline/_ref`` by
+``__graft_entry__.build()`` (git-ignored, travels with the snapshot) — only ``bench.py
+--impl reference`` reads it there, to time the reference itself.
 
 Two shims:
   1. ``torch_geometric`` is not installed: inject a container-only
@@ -18,7 +20,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SPAI_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")      # copy made by __graft_entry__.build()
+
+
+def _default_root() -> str:
+    env = os.environ.get("SPAI_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/preconditioner.py"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available() -> bool:
@@ -84,7 +99,7 @@ def load_reference():
 
 
 def reference_update(n, edge_row, edge_col, edge_val, a_row, a_col, a_val, actions, alpha,
-                     quiet: bool = True):
+                     quiet: bool = True, alpha_tensor: bool = False):
     """Run the reference's own PreconditionerEnv.update on fp32 COO inputs.
 
     Returns dict(reward f64[B], orig_residual, orig_flops, init_nnz, num_actions)."""
@@ -99,7 +114,10 @@ def reference_update(n, edge_row, edge_col, edge_val, a_row, a_col, a_val, actio
         torch.tensor(np.stack([a_row, a_col]), dtype=torch.long),
         torch.tensor(np.asarray(a_val), dtype=torch.float32), (n, n))
     env = ref.PreconditionerEnv(n, init, orig)
-    env.alpha = float(alpha)
+    # alpha_tensor: keep alpha a 0-dim tensor as the live sampler passes it (gflownet.py:183); with
+    # a Python float the reference's inf-ratio branch (preconditioner.py:154,:158) dies at :64
+    # ('float' object has no attribute 'to')
+    env.alpha = torch.tensor(float(alpha)) if alpha_tensor else float(alpha)
     acts = torch.tensor(np.asarray(actions), dtype=torch.long)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink) if quiet else contextlib.nullcontext():

@@ -22,12 +22,12 @@ from gflownet_spai_b200 import synth  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 
-def run_case(name, n, er, ec, ev, ar, ac, av, actions, alpha):
+def run_case(name, n, er, ec, ev, ar, ac, av, actions, alpha, alpha_tensor=False):
     er, ec, ar, ac = (np.asarray(x, dtype=np.int64) for x in (er, ec, ar, ac))
     ev = np.asarray(ev, dtype=np.float32)
     av = np.asarray(av, dtype=np.float32)
     actions = np.asarray(actions, dtype=np.int64)
-    out = ref_shim.reference_update(n, er, ec, ev, ar, ac, av, actions, alpha)
+    out = ref_shim.reference_update(n, er, ec, ev, ar, ac, av, actions, alpha, alpha_tensor=alpha_tensor)
     m_ptr, m_row, m_col, m_val = [0], [], [], []
     for b in range(actions.shape[0]):
         _, r, c, v = ref_shim.reference_masks_and_indices(n, er, ec, ev, actions[b])
@@ -52,7 +52,25 @@ def pad(rows, fill=-1):
     return np.array([list(r) + [fill] * (t - len(r)) for r in rows], dtype=np.int64)
 
 
+def inf_cases():
+    """Zero baselines: `float('inf')` ratios of preconditioner.py:154 and :158."""
+    rng = np.random.default_rng(99)
+    n = 6
+    er = rng.integers(0, n, 14)
+    ec = rng.integers(0, n, 14)
+    ev = rng.uniform(-1, 1, 14)
+    acts = pad([[14], [0, 3, 14], list(range(14)) + [14]])
+    # 6. A0 = identity: ||A0 A0 - I||_F = 0  ->  residual ratio = inf (:154)
+    run_case("zero_res0", n, er, ec, ev, np.arange(n), np.arange(n), np.ones(n), acts, 0.5, alpha_tensor=True)
+    # 7. A0 with no stored entry: orig_flops = 0  ->  computational ratio = inf (:158)
+    run_case("zero_flops0", n, er, ec, ev, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0), acts, 0.5,
+             alpha_tensor=True)
+
+
 def main():
+    if "--inf-only" in sys.argv:
+        inf_cases()
+        return
     # 1. the 3x3 known-answer case of SURVEY.md §4 (explicit zero, unsorted order)
     er = [2, 0, 1, 0, 2, 1]
     ec = [2, 0, 1, 1, 0, 0]
@@ -117,6 +135,7 @@ def main():
     coo = a.tocoo()
     acts = synth.make_trajectories(r.size, 6, seed0=5)
     run_case("poisson32_k8", a.shape[0], r, c, v, coo.row, coo.col, coo.data, acts, 0.5)
+    inf_cases()
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.spai_abi_version() == 1
+    assert lib.spai_abi_version() == 2
     assert isinstance(lib.spai_last_error(), bytes)
 
 

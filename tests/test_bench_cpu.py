@@ -25,6 +25,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["steps"] == 2 and d["warmup"] == 1 and "workload" in d["config"]
+    # both arms print the same `config` dict (bench.config_dict): static facts of the workload only
+    assert set(d["config"]) == {"workload", "mode", "n", "num_edges", "batch_per_gpu", "alpha", "max_deleted_fraction",
+                                "trajectories", "parallelism", "l2", "timing"}
+    it = d["reference_itself"]
+    assert it is None or "error" in it or (it["as_is_patterns_per_s"] > 0 and it["minus_gc_patterns_per_s"] > 0)
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
