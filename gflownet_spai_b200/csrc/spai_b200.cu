@@ -1352,7 +1352,17 @@ struct K0bScratch {
   uint16_t* hdr = nullptr;       // [group][nchunks][C + 1]
   int64_t group = 0, ld_stage = 0, nchunks = 0;
   int C = 0;
+  int threads = K0B_THREADS;     // sort CTA size; a chunk is 16 ids per thread
+  int64_t chunk() const { return (int64_t)threads * K0B_IDS; }
 };
+// sort CTA size: SPAI_K0B_THREADS=256|512 (A/B); 256-thread CTAs need C <= 256
+static inline int k0b_threads(int64_t C) {
+  const char* e = getenv("SPAI_K0B_THREADS");
+  int t = e ? atoi(e) : 256;               // measured (cfg3, B = 1024): sort 2.13 ms with 256 threads, 2.58 ms with 512
+  if (t != 256 && t != 512) t = 256;
+  if (C > t) t = K0B_THREADS;
+  return t;
+}
 static inline bool k0_fits_smem(int64_t W) { return W * 4 <= K0S_MAX_SMEM; }
 static inline int k0_variant() {             // A/B + test switch, read per call
   const char* e = getenv("SPAI_K0_VARIANT");
@@ -1365,22 +1375,23 @@ static inline bool k0b_applies(const Pattern& P, int64_t T) {
   if (C > K0B_MAX_SEGS) return false;
   return !k0_fits_smem(P.words()) || k0_variant() == 3;
 }
-// trajectories per sort+build launch pair: the staged ids of a group (2 bytes each) should stay in L2
-// between the two passes; SPAI_K0B_GROUP overrides (A/B)
+// trajectories per sort+build launch pair. Measured on B200 (cfg3, B = 1024, tools/ab_k0.py): small groups whose
+// staged ids would stay in L2 LOSE — 8: 12.3 ms, 16: 7.8, 32: 6.5, 64: 5.5, whole batch: 4.5 ms (launch tails
+// dominate, the 2 + 2 staged bytes per id are cheap next to them) — so a group is as large as 8 GiB of staged
+// ids allow; SPAI_K0B_GROUP overrides (A/B).
 static int64_t k0b_group(int64_t bc, int64_t T, int64_t C) {
   const char* e = getenv("SPAI_K0B_GROUP");
   const int64_t forced = e ? atoll(e) : 0;
   if (forced > 0) return std::min(bc, forced);
-  const int64_t tasks = ceil_div(C, (int64_t)K0B_R);
-  int64_t g = ((int64_t)96 << 20) / std::max<int64_t>(2 * T, 1);       // <= 96 MB of staged ids at full length
-  g = std::max(g, ceil_div((int64_t)2 * 148, tasks));                   // >= 2 build CTAs per SM
-  g = std::max<int64_t>(g, 8);
-  return std::min(bc, g);
+  (void)C;
+  const int64_t g = ((int64_t)8 << 30) / std::max<int64_t>(2 * round_up(std::max<int64_t>(T, 1), K0B_CHUNK_MAX), 1);
+  return std::min(bc, std::max<int64_t>(g, 32));
 }
 static void k0b_plan(const Pattern& P, int64_t bc, int64_t T, K0bScratch* sc) {
   sc->C = (int)ceil_div(P.E, (int64_t)1 << K0B_SEG_SHIFT);
-  sc->nchunks = ceil_div(T, (int64_t)K0B_CHUNK);
-  sc->ld_stage = sc->nchunks * K0B_CHUNK;
+  sc->threads = k0b_threads(sc->C);
+  sc->nchunks = ceil_div(T, sc->chunk());
+  sc->ld_stage = sc->nchunks * sc->chunk();
   sc->group = k0b_group(bc, T, sc->C);
 }
 static int64_t k0b_bytes(const K0bScratch& sc) {
@@ -1409,29 +1420,54 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
     *nnz_fused = true;
   } else if (sc && sc->stage && k0b_applies(P, T)) {
     const int C = sc->C;
-    const size_t ssm = k0b_sort_smem(C);
+    const int TH = sc->threads;
+    const size_t ssm = k0b_sort_smem(C, TH);
     const size_t bsm = (size_t)std::min<int64_t>((int64_t)K0B_R, C) * K0B_SEG_WORDS * 4;
     const int tasks = (int)ceil_div(C, (int64_t)K0B_R);
-    SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0b_sort_smem(K0B_MAX_SEGS)));
-    SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0b_sort_smem(K0B_MAX_SEGS)));
+    const int smax = (int)k0b_sort_smem(K0B_MAX_SEGS, K0B_THREADS);
+#define SPAI_K0B_ATTR(IDT, MAP, THR) \
+  SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<IDT, MAP, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax))
+    SPAI_K0B_ATTR(int64_t, false, 512); SPAI_K0B_ATTR(int64_t, true, 512); SPAI_K0B_ATTR(int32_t, false, 512); SPAI_K0B_ATTR(int32_t, true, 512);
+    SPAI_K0B_ATTR(int64_t, false, 256); SPAI_K0B_ATTR(int64_t, true, 256); SPAI_K0B_ATTR(int32_t, false, 256); SPAI_K0B_ATTR(int32_t, true, 256);
+#undef SPAI_K0B_ATTR
     SPAI_CUDA(cudaFuncSetAttribute(k0b_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
     SPAI_CUDA(cudaMemsetAsync(nnz0, 0, (size_t)bc * 8, st));
+    static const bool timing = getenv("SPAI_K0B_TIMING") != nullptr;      // per-pass device times on stderr (diagnostic)
+    cudaEvent_t ev[3] = {};
+    float ms_sort = 0, ms_build = 0;
+    if (timing) for (auto& e : ev) cudaEventCreate(&e);
     for (int64_t g0 = 0; g0 < bc; g0 += sc->group) {
       const int64_t gb = std::min(sc->group, bc - g0);
       const int64_t nblk = gb * sc->nchunks;
       if (nblk >= ((int64_t)1 << 31) || gb * tasks >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
       const int32_t* rl = row_len ? row_len + g0 : nullptr;
-      if (elem == 8)
-        k0b_sort_kernel<int64_t><<<(unsigned)nblk, K0B_THREADS, ssm, st>>>(a64 + g0 * act_ld, T, act_ld, rl, eslot, P.E, C,
-                                                                         sc->stage, sc->ld_stage, sc->hdr, sc->nchunks);
-      else
-        k0b_sort_kernel<int32_t><<<(unsigned)nblk, K0B_THREADS, ssm, st>>>(a32 + g0 * act_ld, T, act_ld, rl, eslot, P.E, C,
-                                                                         sc->stage, sc->ld_stage, sc->hdr, sc->nchunks);
+      if (timing) cudaEventRecord(ev[0], st);
+#define SPAI_K0B_SORT(IDT, PTR, MAP, THR)                                                                         \
+  k0b_sort_kernel<IDT, MAP, THR><<<(unsigned)nblk, THR, ssm, st>>>(PTR + g0 * act_ld, T, act_ld, rl, eslot, P.E, C, \
+                                                                   sc->stage, sc->ld_stage, sc->hdr, sc->nchunks)
+#define SPAI_K0B_SORT2(IDT, PTR, MAP) do { if (TH == 256) SPAI_K0B_SORT(IDT, PTR, MAP, 256); else SPAI_K0B_SORT(IDT, PTR, MAP, 512); } while (0)
+      if (elem == 8) { if (eslot) SPAI_K0B_SORT2(int64_t, a64, true); else SPAI_K0B_SORT2(int64_t, a64, false); }
+      else { if (eslot) SPAI_K0B_SORT2(int32_t, a32, true); else SPAI_K0B_SORT2(int32_t, a32, false); }
+#undef SPAI_K0B_SORT2
+#undef SPAI_K0B_SORT
       SPAI_CUDA(cudaGetLastError()); ++*launches;
+      if (timing) cudaEventRecord(ev[1], st);
       k0b_build_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
           sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
-          reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks);
+          reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk());
       SPAI_CUDA(cudaGetLastError()); ++*launches;
+      if (timing) {
+        cudaEventRecord(ev[2], st);
+        cudaEventSynchronize(ev[2]);
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); ms_sort += t;
+        cudaEventElapsedTime(&t, ev[1], ev[2]); ms_build += t;
+      }
+    }
+    if (timing) {
+      fprintf(stderr, "[k0b] B=%lld T=%lld C=%d threads=%d group=%lld: sort %.3f ms, build %.3f ms\n", (long long)bc,
+              (long long)T, C, TH, (long long)sc->group, ms_sort, ms_build);
+      for (auto& e : ev) cudaEventDestroy(e);
     }
     *nnz_fused = true;
   } else {
