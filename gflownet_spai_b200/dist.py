@@ -12,7 +12,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_rows", "gather_rewards"]
+__all__ = ["shard_bounds", "shard_rows", "gather_rewards", "reward_row_sharded", "dp_trajectory_balance_loss",
+           "allreduce_gradients", "data_parallel_step"]
 
 
 def shard_bounds(batch: int, world: int, rank: int) -> tuple[int, int]:
@@ -62,3 +63,123 @@ def reward_row_sharded(ctx, actions: torch.Tensor, alpha: float, mode: str = "co
     if world > 1:
         dist.all_reduce(res2, op=dist.ReduceOp.SUM, group=group)
     return ctx.finalize_rewards(res2, nnz, alpha, dtype)
+
+
+# --------------------------------------------------------------------------
+# Data-parallel training step (the north star's last collective): trajectories
+# are sharded, the trajectory-balance loss is formed shard-locally and only
+# scalars + the policy gradients cross NVLink.
+# --------------------------------------------------------------------------
+def dp_trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs, global_batch: int, group=None):
+    """Shard-local surrogate of the reference's mean trajectory-balance loss
+    (gflownet/utils.py:228-278) over the GLOBAL batch.
+
+    Returns (surrogate, loss_value): summing the gradients of `surrogate` over the ranks
+    (all-reduce, `allreduce_gradients`) gives exactly the gradient of the single-process loss on
+    the concatenated batch, and `loss_value` (a detached scalar, identical on every rank) is that
+    loss. The reference subtracts the BATCH maximum of the summed log-probabilities on each side
+    (utils.py:262-267) and that maximum carries gradient; here the two maxima and the sum of the
+    residuals are exchanged as scalars (two tiny all-reduces) and the maximum's gradient is
+    attached on the rank that owns the arg-max trajectory.
+    Shapes as in the reference: rewards [b], fwd_probs / back_probs [b, T] for this rank's b
+    trajectories (b may be 0); global_batch = sum of b over the ranks."""
+    eps = 1e-9
+    dt, dev = fwd_probs.dtype, fwd_probs.device
+    total_flow = total_flow.to(dev).to(dt)
+    rewards = rewards.to(dev).to(dt)
+    back_probs = back_probs.to(dev).to(dt)
+    lf = torch.log(fwd_probs + eps).sum(dim=-1)
+    lb = torch.log(back_probs + eps).sum(dim=-1)
+    on = dist.is_initialized() and dist.get_world_size(group) > 1
+    neg = torch.finfo(dt).min
+    mx = torch.stack([lf.detach().max() if lf.numel() else torch.tensor(neg, dtype=dt, device=dev),
+                      lb.detach().max() if lb.numel() else torch.tensor(neg, dtype=dt, device=dev)])
+    if on:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    resid = (torch.log(total_flow + eps) + (lf - mx[0])) - (torch.log(rewards + eps) + (lb - mx[1]))
+    stats = torch.stack([resid.detach().sum(), (resid.detach() ** 2).sum()])
+    if on:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    r_sum, loss_value = stats[0], stats[1] / global_batch
+    surrogate = (resid ** 2).sum() / global_batch
+    # d loss / d max_f = -(2/B) * sum_b resid_b ; d loss / d max_b = +(2/B) * sum_b resid_b.
+    # torch.max routes its gradient to the first arg-max element; ties across ranks go to the lowest rank.
+    me = dist.get_rank(group) if on else 0
+    far = 1 << 30
+    owner = torch.tensor([me if (v.numel() and bool(v.detach().max() == mx[i])) else far
+                          for i, v in enumerate((lf, lb))], device=dev, dtype=torch.int64)
+    if on:                                   # every rank takes part, whatever its shard holds
+        dist.all_reduce(owner, op=dist.ReduceOp.MIN, group=group)
+    for side, vec, sign in ((0, lf, -1.0), (1, lb, 1.0)):
+        if int(owner[side]) == me and vec.requires_grad:
+            surrogate = surrogate + sign * (2.0 / global_batch) * r_sum * vec[torch.argmax(vec.detach())]
+    return surrogate, loss_value.detach()
+
+
+def allreduce_gradients(params, group=None, bucket_bytes: int = 64 << 20, average: bool = False):
+    """Sum (or average) the gradients of `params` over the ranks in flat buckets of at most
+    `bucket_bytes` (the dominant tensor is the forward policy's fc weight, hid x (E+1),
+    policy.py:30): one all-reduce per bucket, issued back to back (async) and awaited together,
+    so a bucket's reduction overlaps the packing of the next. Parameters without a gradient
+    on some rank (an empty shard) contribute zeros. Returns the number of bytes reduced."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    if world == 1:
+        return 0
+    buckets, cur, cur_bytes = [], [], 0
+    for p in params:
+        nb = p.grad.numel() * p.grad.element_size()
+        if cur and (cur_bytes + nb > bucket_bytes or p.grad.dtype != cur[0].grad.dtype or p.grad.device != cur[0].grad.device):
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += nb
+    if cur:
+        buckets.append(cur)
+    pending, total = [], 0
+    for bk in buckets:
+        flat = torch.cat([p.grad.reshape(-1) for p in bk])
+        total += flat.numel() * flat.element_size()
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bk))
+    for work, flat, bk in pending:
+        work.wait()
+        if average:
+            flat.div_(world)
+        off = 0
+        for p in bk:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+    return total
+
+
+def data_parallel_step(model, optimizer, s0_shard, global_batch: int, group=None, generator=None,
+                       method: str = "step", bucket_bytes: int = 64 << 20):
+    """One epoch of the reference's training loop (GFlowNet100.py:291-315) with the batch sharded
+    over the ranks: this rank samples and scores `len(s0_shard)` trajectories on its GPU
+    (`model.sample_states`, rewards by the SPAI kernels), forms the shard-local surrogate of the
+    global trajectory-balance loss, all-reduces the policy gradients and steps the optimiser
+    (identical parameters on every rank before and after). Returns (loss, log); the per-trajectory
+    rewards stay on the rank (gather them with `gather_rewards` only for logging)."""
+    from .sampler import trajectory_balance_loss
+    log = model.sample_states(s0_shard, return_log=True, generator=generator, method=method)
+    params = [p for p in model.parameters() if p.requires_grad]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        loss = trajectory_balance_loss(log.total_flow, log.rewards, log.fwd_probs, log.back_probs)
+        value = loss.detach()
+    else:
+        loss, value = dp_trajectory_balance_loss(log.total_flow, log.rewards, log.fwd_probs, log.back_probs,
+                                                 global_batch, group)
+    if bool(torch.isnan(value) | torch.isinf(value)):          # GFlowNet100.py:306-308: skip the step
+        optimizer.zero_grad()
+        return value, log
+    loss.backward()
+    allreduce_gradients(params, group, bucket_bytes)
+    optimizer.step()
+    optimizer.zero_grad()
+    return value, log
