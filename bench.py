@@ -665,6 +665,32 @@ def run_b200_arm(args):
                         "separately for the row-sweep kernels only, because the batch re-uses every gathered row from "
                         "shared memory and G/time exceeds the HBM peak by design."}
 
+    # ---- the other collective of the training step: the policy-gradient all-reduce (N > 1)
+    dp_training = None
+    if world > 1:
+        from gflownet_spai_b200.dist import allreduce_gradients
+        hid, a_n = 4, p.num_edges + 1                       # GFlowNet100.py:180 hidden_dim; policy.py:30 fc = hid x A
+        shapes = [(a_n, hid), (a_n,), (a_n, hid), (a_n,), (4 * hid, hid + 1), (4 * hid,)]   # fwd fc, bwd fc, LSTM
+        params = [torch.nn.Parameter(torch.zeros(sh, device=dev)) for sh in shapes]
+        for q in params:
+            q.grad = torch.ones_like(q)
+        for _ in range(3):
+            nbytes = allreduce_gradients(params)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            allreduce_gradients(params)
+        g1.record()
+        barrier()
+        t_g = torch.tensor([g0.elapsed_time(g1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+        dp_training = {"grad_bytes": int(nbytes), "allreduce_ms": float(t_g),
+                       "algbw_gbps": nbytes / float(t_g) / 1e6, "reward_step_ms": dev_ms / args.steps,
+                       "shapes": "forward + backward policy fc = hid x (E+1) with hid = 4 (GFlowNet100.py:180, policy.py:30), "
+                                 "one flat bucket, NCCL all-reduce (dist.allreduce_gradients)"}
+        del params
+
     # ---- end to end through the host entry point (pinned host actions in, rewards out)
     e2e = None
     if not args.no_e2e:
@@ -834,6 +860,7 @@ def run_b200_arm(args):
             "roofline": roofline,
             "kernels": kern,
             "e2e": e2e,
+            "dp_training": dp_training,
             "cpu_baseline": cpu,
             "parity_check": parity,
             "extras": extras,

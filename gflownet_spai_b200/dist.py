@@ -70,6 +70,19 @@ def reward_row_sharded(ctx, actions: torch.Tensor, alpha: float, mode: str = "co
 # are sharded, the trajectory-balance loss is formed shard-locally and only
 # scalars + the policy gradients cross NVLink.
 # --------------------------------------------------------------------------
+def _all_reduce(t: torch.Tensor, op, group=None, async_op: bool = False):
+    """all_reduce that also serves host tensors under NCCL (staged through the current CUDA device).
+    Returns (work or None, tensor holding the result once the work is done, original)."""
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:
+        staged = t.to(torch.device("cuda", torch.cuda.current_device()))
+        work = dist.all_reduce(staged, op=op, group=group, async_op=async_op)
+        if not async_op:
+            t.copy_(staged)
+        return work, staged, t
+    work = dist.all_reduce(t, op=op, group=group, async_op=async_op)
+    return work, t, t
+
+
 def dp_trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs, global_batch: int, group=None):
     """Shard-local surrogate of the reference's mean trajectory-balance loss
     (gflownet/utils.py:228-278) over the GLOBAL batch.
@@ -95,11 +108,11 @@ def dp_trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs, globa
     mx = torch.stack([lf.detach().max() if lf.numel() else torch.tensor(neg, dtype=dt, device=dev),
                       lb.detach().max() if lb.numel() else torch.tensor(neg, dtype=dt, device=dev)])
     if on:
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        _all_reduce(mx, dist.ReduceOp.MAX, group)
     resid = (torch.log(total_flow + eps) + (lf - mx[0])) - (torch.log(rewards + eps) + (lb - mx[1]))
     stats = torch.stack([resid.detach().sum(), (resid.detach() ** 2).sum()])
     if on:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(stats, dist.ReduceOp.SUM, group)
     r_sum, loss_value = stats[0], stats[1] / global_batch
     surrogate = (resid ** 2).sum() / global_batch
     # d loss / d max_f = -(2/B) * sum_b resid_b ; d loss / d max_b = +(2/B) * sum_b resid_b.
@@ -109,7 +122,7 @@ def dp_trajectory_balance_loss(total_flow, rewards, fwd_probs, back_probs, globa
     owner = torch.tensor([me if (v.numel() and bool(v.detach().max() == mx[i])) else far
                           for i, v in enumerate((lf, lb))], device=dev, dtype=torch.int64)
     if on:                                   # every rank takes part, whatever its shard holds
-        dist.all_reduce(owner, op=dist.ReduceOp.MIN, group=group)
+        _all_reduce(owner, dist.ReduceOp.MIN, group)
     for side, vec, sign in ((0, lf, -1.0), (1, lb, 1.0)):
         if int(owner[side]) == me and vec.requires_grad:
             surrogate = surrogate + sign * (2.0 / global_batch) * r_sum * vec[torch.argmax(vec.detach())]
@@ -145,7 +158,8 @@ def allreduce_gradients(params, group=None, bucket_bytes: int = 64 << 20, averag
     for bk in buckets:
         flat = torch.cat([p.grad.reshape(-1) for p in bk])
         total += flat.numel() * flat.element_size()
-        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bk))
+        work, staged, _ = _all_reduce(flat, dist.ReduceOp.SUM, group, async_op=True)
+        pending.append((work, staged, bk))
     for work, flat, bk in pending:
         work.wait()
         if average:
@@ -153,7 +167,7 @@ def allreduce_gradients(params, group=None, bucket_bytes: int = 64 << 20, averag
         off = 0
         for p in bk:
             n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))        # (device -> host when the gradients live on the host)
             off += n
     return total
 
