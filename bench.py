@@ -92,6 +92,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = None
         self._nvml = None
+        self.gate = True            # samples are recorded only while the gate is open (timed regions)
 
     def start(self):
         try:
@@ -115,6 +116,9 @@ class ClockSampler:
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
         }
         while not self._stop.is_set():
+            if not self.gate:
+                time.sleep(0.001)
+                continue
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
                 bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
@@ -181,7 +185,7 @@ def pin_to_gpu_numa_node(index):
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            return {"numa_node": node, "note": "the platform reports no NUMA affinity for this GPU"}
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -191,9 +195,9 @@ def pin_to_gpu_numa_node(index):
         if cpus:
             os.sched_setaffinity(0, cpus)
             return {"numa_node": node, "cpus": len(cpus)}
-    except Exception:
-        return None
-    return None
+        return {"numa_node": node, "cpus": 0}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def measured_peak():
@@ -473,6 +477,10 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
     parity = {}
     first = True
     gen_s = 0.0
+    chunk_log = []
+    sampler = ClockSampler(local)
+    sampler.gate = False
+    sampler.start()
     for c0 in range(lo, hi, chunk):
         c1 = min(hi, c0 + chunk)
         tg = time.perf_counter()
@@ -497,18 +505,28 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
                     except Exception as exc:
                         parity[f"{mode}/{dt}"] = {"error": f"{type(exc).__name__}: {exc}"}
                 ph_acc[(mode, dt)] = phase_times(ctx, call, flush, 2)
+            # the host-side trajectory generation leaves the GPU idle for seconds and its clocks drop to
+            # idle (observed: one 32 ms call took 637 ms at 120 MHz): bring them back before timing
+            warm = lambda: ctx.reward_batch(sub[:96], 0.5, mode, tdt, want=("reward",), lengths=sl[:96])
+            for _ in range(3):
+                warm()
+                flush.zero_()
+            torch.cuda.synchronize()
             reps = 3 if not strong else 1
             ms = 0.0
             for _ in range(reps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                sampler.gate = True
                 e0.record()
                 call()
                 e1.record()
                 torch.cuda.synchronize()
+                sampler.gate = False
                 ms += e0.elapsed_time(e1) / reps
             scale_up = (acts.shape[0] / sub.shape[0])
             tot_ms[(mode, dt)] += ms * scale_up
+            chunk_log.append((f"{mode}/{dt}", int(acts.shape[0]), int(acts.shape[1]), round(ms * scale_up, 3)))
         first = False
         del acts, lens
     for (mode, dt) in variants:
@@ -518,6 +536,11 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(ids, op=dist.ReduceOp.SUM)
         ms = float(t)
+        per_rank = [tot_ms[(mode, dt)]]
+        if world > 1:
+            allms = [None] * world
+            dist.all_gather_object(allms, tot_ms[(mode, dt)])
+            per_rank = [float(x) for x in allms]
         ph = ph_acc[(mode, dt)] or {}
         comp = float(ids) * 8.0 + total * (W * 4.0 + 8.0)
         k0_bytes_rank = valid_ids * 8.0 + (hi - lo) * W * 4.0
@@ -525,6 +548,7 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
         k0_ms_rank = tot_ms[(mode, dt)] * (ph.get("masks", 0.0) / share_tot) if ph else None
         res["variants"][f"{mode}/{dt}"] = {
             "ms_per_step": ms, "patterns_per_s": total / (ms / 1e3), "row_solves_per_s": total * p.n / (ms / 1e3),
+            "per_rank_ms": per_rank,
             "kernel_share": {k: v / share_tot for k, v in ph.items()} if ph else None,
             "reward_kernel": reward_kernel_name(ctx, p, mode, min(chunk, hi - lo), tmax_seen),
             "compulsory_bytes_per_step": comp, "compulsory_frac_of_hbm_peak": comp / (ms / 1e3) / 1e9 / peak,
@@ -532,6 +556,20 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
             "k0_frac_of_hbm_peak_on_valid_bytes": (k0_bytes_rank / (k0_ms_rank / 1e3) / 1e9 / peak) if k0_ms_rank else None,
             "note": ("ls_gram timed on 256 of every 1024 patterns and scaled" if (mode == "ls_gram" and name == "cfg4") else None),
         }
+    if world > 1:
+        logs = [None] * world
+        dist.all_gather_object(logs, chunk_log[:24])
+        res["chunks_per_rank"] = logs
+    else:
+        res["chunks_per_rank"] = [chunk_log[:24]]
+    clk = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clk)
+        sm = [c["sm_mhz"] for c in allc if c and c["sm_mhz"]]
+        clk = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clk["sm_max_mhz"],
+               "reasons": sorted({r for c in allc if c for r in c["reasons"]}), "samples": sum(c["samples"] for c in allc if c)}
+    res["clocks"] = clk
     res["max_trajectory_len"] = tmax_seen
     res["trajectory_generation_s_untimed"] = gen_s
     res["parity_check"] = parity or None
