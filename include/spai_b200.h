@@ -221,6 +221,45 @@ int spai_finalize_rewards_dev(spai_ctx* ctx, const double* res2_dev, const int64
 int spai_pack_taken_dev(spai_ctx* ctx, const float* keys_dev, int64_t keys_ld, int64_t A, int64_t B,
                         uint32_t* taken_dev, int64_t words_ld, int32_t* length_dev, void* stream);
 
+/* ---- Device-side ingest: the step immediately before the reward path. ----
+ * All array arguments are DEVICE pointers on `device`; outputs are caller-allocated; totals that
+ * size a later allocation come back through a HOST pointer (the call synchronises `stream`).
+ * Rows are limited to 512 entries (working sets live in shared memory): SPAI_ERR_UNSUPPORTED beyond.
+ *
+ * gflownet/utils.py:54-63 (`market_matrix_to_sparse_tensor`: scipy COO -> torch sparse) followed by
+ * the coalesce the reference's sparse ops apply: COO (any order, repeated coordinates summed in
+ * entry order) -> CSR with ascending columns. ptr_dev i32[n+1], col/val sized for nnz entries. */
+int spai_ingest_coo_to_csr_dev(int device, int64_t n, int64_t nnz, const int64_t* row_dev,
+                               const int64_t* col_dev, const double* val_dev, int32_t* ptr_dev,
+                               int32_t* col_out_dev, double* val_out_dev, int64_t* nnz_out_host,
+                               void* stream);
+/* GFlowNet100.py:139-141 (`LU = L @ U`, the initial matrix from sparse factors): CSR SpGEMM C = A*B in
+ * two calls: _count fills c_ptr_dev i32[n+1] and returns nnz(C); _fill writes columns (ascending) and
+ * values (products summed in the order of A's row entries: deterministic). a_val / b_val may be NULL
+ * (pattern product, all ones). */
+int spai_ingest_spgemm_count_dev(int device, int64_t n, const int32_t* a_ptr, const int32_t* a_col,
+                                 const int32_t* b_ptr, const int32_t* b_col, int32_t* c_ptr_dev,
+                                 int64_t* c_nnz_host, void* stream);
+int spai_ingest_spgemm_fill_dev(int device, int64_t n, const int32_t* a_ptr, const int32_t* a_col,
+                                const double* a_val, const int32_t* b_ptr, const int32_t* b_col,
+                                const double* b_val, const int32_t* c_ptr_dev, int32_t* c_col_dev,
+                                double* c_val_dev, void* stream);
+/* Candidate superset S of SURVEY.md 8d (what the drivers' "initial matrix" pattern stands for):
+ *   order 0: S(i) = first k entries of pattern(I) U pattern(A) U ... U pattern(A^max_power) (i,:) ordered
+ *            by (graph distance from i, column id);
+ *   order 1: S(i) = first k entries of pattern(A)(i,:) ordered by (|col - i|, col).
+ * Output row-major COO with ascending columns per row: s_ptr_dev i64[n+1], s_row_dev / s_col_dev i64
+ * sized for n*k entries (may be NULL to get only the counts), total through s_nnz_host. */
+int spai_ingest_superset_dev(int device, int64_t n, const int32_t* a_ptr, const int32_t* a_col, int k,
+                             int max_power, int order, int64_t* s_ptr_dev, int64_t* s_row_dev,
+                             int64_t* s_col_dev, int64_t* s_nnz_host, void* stream);
+/* Initial values on S: omega * sum_{j < terms} (I - omega*A)^j restricted to S, omega = 1 / max_i sum_j |A_ij|
+ * (a truncated Neumann series of A^-1; stands in for the drivers' spilu factors, GFlowNet100.py:126-153).
+ * fp64; val_out_dev f64[nnz(S)] in the order of s_col_dev; omega_host (optional) receives omega. */
+int spai_ingest_neumann_dev(int device, int64_t n, const int32_t* a_ptr, const int32_t* a_col,
+                            const double* a_val, const int64_t* s_ptr_dev, const int64_t* s_col_dev,
+                            int terms, double* omega_host, double* val_out_dev, void* stream);
+
 /* Per-kernel device time of the LAST reward call on this context, in ms,
  * measured with CUDA events on the caller's stream (masks, transpose, reward
  * kernel, finalize) and the number of kernels launched by it. */
