@@ -29,7 +29,7 @@ EXPORTS = [
     "spai_ctx_last_timing", "spai_ctx_set_deletion_hint",
     "spai_reward_batch_host_len", "spai_reward_batch_dev_len",
     "spai_ingest_coo_to_csr_dev", "spai_ingest_spgemm_count_dev", "spai_ingest_spgemm_fill_dev",
-    "spai_ingest_superset_dev", "spai_ingest_neumann_dev",
+    "spai_ingest_superset_dev", "spai_ingest_neumann_dev", "spai_ingest_csr_drop_zeros_dev",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
     lib.spai_ingest_coo_to_csr_dev.argtypes = [i32, i64, i64, pv, pv, pv, pv, pv, pv, p64, pv]
     lib.spai_ingest_spgemm_count_dev.argtypes = [i32, i64, pv, pv, pv, pv, pv, p64, pv]
     lib.spai_ingest_spgemm_fill_dev.argtypes = [i32, i64, pv, pv, pv, pv, pv, pv, pv, pv, pv, pv]
+    lib.spai_ingest_csr_drop_zeros_dev.argtypes = [i32, i64, pv, pv, pv, pv, pv, pv, p64, pv]
     lib.spai_ingest_superset_dev.argtypes = [i32, i64, pv, pv, i32, i32, i32, pv, pv, pv, p64, pv]
     lib.spai_ingest_neumann_dev.argtypes = [i32, i64, pv, pv, pv, pv, pv, i32, pd, pv, pv]
     lib.spai_kept_mask_dev.argtypes = [pv, pv, i64, i64, i64, pv, pv]

@@ -238,7 +238,9 @@ k5_spgemm_kernel(int64_t n, const int* __restrict__ aptr, const int* __restrict_
         const int at = atomicAdd(&cnt_s[w], 1);
         if (at < K5_LIST) r.slot_of[at] = s;
       }
-      if (FILL) r.val[s] += a * (bval ? bval[q] : 1.0);      // columns of one B row are distinct: no race
+      // separate multiply and add (no FMA contraction): bit-identical to scipy's csr_matmat, which matters
+      // because the product is pruned of EXACT zeros afterwards. Columns of one B row are distinct: no race.
+      if (FILL) r.val[s] = __dadd_rn(r.val[s], __dmul_rn(a, bval ? bval[q] : 1.0));
     }
     __syncwarp();
   }
@@ -252,6 +254,25 @@ k5_spgemm_kernel(int64_t n, const int* __restrict__ aptr, const int* __restrict_
   for (int t = lane; t < m; t += 32) {
     ccol[o + t] = (int)(sk[w][t] >> 32);
     cval[o + t] = r.val[(unsigned)sk[w][t]];
+  }
+}
+
+// scipy's csr_matmat (what the reference's `L @ U` runs) stores only results != 0: drop exact zeros.
+__global__ void k5_count_nonzero_kernel(int64_t n, const int* __restrict__ ptr, const double* __restrict__ val,
+                                        int* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) c += val[p] != 0.0;
+    cnt[i] = c;
+  }
+}
+__global__ void k5_copy_nonzero_kernel(int64_t n, const int* __restrict__ ptr, const int* __restrict__ col,
+                                       const double* __restrict__ val, const int* __restrict__ optr,
+                                       int* __restrict__ ocol, double* __restrict__ oval) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int o = optr[i];
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p)
+      if (val[p] != 0.0) { ocol[o] = col[p]; oval[o] = val[p]; ++o; }
   }
 }
 

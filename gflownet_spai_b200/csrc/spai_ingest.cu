@@ -148,6 +148,30 @@ int spai_ingest_spgemm_fill_dev(int device, int64_t n, const int32_t* a_ptr, con
   return check_flag(ovf, st, "spgemm: a row of the product has more than 512 entries", SPAI_ERR_UNSUPPORTED);
 }
 
+int spai_ingest_csr_drop_zeros_dev(int device, int64_t n, const int32_t* ptr, const int32_t* col, const double* val,
+                                   int32_t* out_ptr_dev, int32_t* out_col_dev, double* out_val_dev,
+                                   int64_t* nnz_out_host, void* stream) {
+  if (n <= 0 || !ptr || !out_ptr_dev || !nnz_out_host) {
+    set_error("spai_ingest_csr_drop_zeros_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  Guard g(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Tmp tmp;
+  int* cnt = nullptr;
+  SPAI_TRY(tmp.get(&cnt, n));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  k5_count_nonzero_kernel<<<blocks, 256, 0, st>>>(n, ptr, val, cnt);
+  SPAI_TRY(scan<int>(cnt, n, out_ptr_dev, tmp, st));
+  if (out_col_dev && out_val_dev) k5_copy_nonzero_kernel<<<blocks, 256, 0, st>>>(n, ptr, col, val, out_ptr_dev, out_col_dev, out_val_dev);
+  SPAI_CUDA(cudaGetLastError());
+  int32_t total = 0;
+  SPAI_CUDA(cudaMemcpyAsync(&total, out_ptr_dev + n, 4, cudaMemcpyDeviceToHost, st));
+  SPAI_CUDA(cudaStreamSynchronize(st));
+  *nnz_out_host = total;
+  return SPAI_OK;
+}
+
 int spai_ingest_superset_dev(int device, int64_t n, const int32_t* a_ptr, const int32_t* a_col, int k, int max_power,
                              int order, int64_t* s_ptr_dev, int64_t* s_row_dev, int64_t* s_col_dev,
                              int64_t* s_nnz_host, void* stream) {

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-__all__ = ["CsrDev", "coo_to_csr", "spgemm", "superset_pattern", "neumann_values", "read_matrix_market"]
+__all__ = ["CsrDev", "coo_to_csr", "spgemm", "drop_zeros", "superset_pattern", "neumann_values", "read_matrix_market"]
 
 
 class CsrDev:
@@ -68,8 +68,22 @@ def coo_to_csr(n: int, row: torch.Tensor, col: torch.Tensor, val: torch.Tensor) 
     return CsrDev(n, ptr, ocol[: total.value], oval[: total.value])
 
 
-def spgemm(a: CsrDev, b: CsrDev) -> CsrDev:
-    """C = A @ B (CSR, columns ascending, deterministic summation order)."""
+def drop_zeros(a: CsrDev) -> CsrDev:
+    """Remove stored entries that are exactly 0 (what scipy's sparse product does)."""
+    lib = _lib.load()
+    dev = a.ptr.device
+    optr = torch.empty(a.n + 1, dtype=torch.int32, device=dev)
+    ocol = torch.empty(max(a.nnz, 1), dtype=torch.int32, device=dev)
+    oval = torch.empty(max(a.nnz, 1), dtype=torch.float64, device=dev)
+    total = C.c_int64(0)
+    check(lib.spai_ingest_csr_drop_zeros_dev(dev.index, a.n, _p(a.ptr), _p(a.col), _p(a.val), _p(optr), _p(ocol), _p(oval),
+                                             C.byref(total), _stream(dev)), "spai_ingest_csr_drop_zeros_dev")
+    return CsrDev(a.n, optr, ocol[: total.value], oval[: total.value])
+
+
+def spgemm(a: CsrDev, b: CsrDev, prune_zeros: bool = True) -> CsrDev:
+    """C = A @ B (CSR, columns ascending, deterministic summation order). prune_zeros=True drops
+    results that are exactly 0, as scipy's product (the reference's `L @ U`) does."""
     lib = _lib.load()
     dev = a.ptr.device
     cptr = torch.empty(a.n + 1, dtype=torch.int32, device=dev)
@@ -80,7 +94,8 @@ def spgemm(a: CsrDev, b: CsrDev) -> CsrDev:
     cval = torch.empty(max(total.value, 1), dtype=torch.float64, device=dev)
     check(lib.spai_ingest_spgemm_fill_dev(dev.index, a.n, _p(a.ptr), _p(a.col), _p(a.val), _p(b.ptr), _p(b.col), _p(b.val),
                                           _p(cptr), _p(ccol), _p(cval), _stream(dev)), "spai_ingest_spgemm_fill_dev")
-    return CsrDev(a.n, cptr, ccol[: total.value], cval[: total.value])
+    out = CsrDev(a.n, cptr, ccol[: total.value], cval[: total.value])
+    return drop_zeros(out) if prune_zeros else out
 
 
 def superset_pattern(a: CsrDev, k: int, max_power: int = 4, order: str = "distance"):

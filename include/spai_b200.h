@@ -244,6 +244,11 @@ int spai_ingest_spgemm_fill_dev(int device, int64_t n, const int32_t* a_ptr, con
                                 const double* a_val, const int32_t* b_ptr, const int32_t* b_col,
                                 const double* b_val, const int32_t* c_ptr_dev, int32_t* c_col_dev,
                                 double* c_val_dev, void* stream);
+/* scipy's product (the reference's `L @ U`) stores only results != 0: drop exact zeros from a CSR.
+ * out_col_dev / out_val_dev sized for the input nnz (in-place is NOT allowed). */
+int spai_ingest_csr_drop_zeros_dev(int device, int64_t n, const int32_t* ptr_dev, const int32_t* col_dev,
+                                   const double* val_dev, int32_t* out_ptr_dev, int32_t* out_col_dev,
+                                   double* out_val_dev, int64_t* nnz_out_host, void* stream);
 /* Candidate superset S of SURVEY.md 8d (what the drivers' "initial matrix" pattern stands for):
  *   order 0: S(i) = first k entries of pattern(I) U pattern(A) U ... U pattern(A^max_power) (i,:) ordered
  *            by (graph distance from i, column id);
