@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=96, help="trajectories in the CPU-baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip the ls-mode side measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the sampler (K4 / K4g) side measurements")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 block of the JSON line")
     ap.add_argument("--configs", default="cfg3,cfg4,cfg5", help="side configs measured after the headline")
     ap.add_argument("--cfg5-batch", type=int, default=16384, help="cfg5 global batch (strong-scaled over the ranks)")
@@ -216,7 +217,7 @@ def _ncu_side_facts(kernel_key):
         with open(path) as f:
             d = json.load(f)
         return {"issue_active_pct": d.get("_issue_active_pct", {}).get(kernel_key),
-                "dram_pct_of_ncu_peak": d.get("_dram_pct_of_ncu_peak", {}).get(kernel_key),
+                "dram_frac_of_measured_peak": d.get("_dram_frac_of_measured_peak", {}).get(kernel_key),
                 "source": d.get("_source")}
     except Exception:
         return None
@@ -580,6 +581,65 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
     return res
 
 
+def sampler_bench(ctx, p, dev, batch, flush):
+    """North-star kernel (4) and SURVEY 8f-1 at the headline config's size: trajectories drawn per second
+    by the whole-trajectory kernels (K4g: taken-bitmask + length, then the ordered ids), the masked
+    categorical single step (K4) per launch, and sample -> reward with everything on the device."""
+    import torch
+    a = p.num_edges + 1
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    logits = (torch.randn(a, generator=g, device=dev) * 0.25).contiguous()     # near-uniform policy (early training)
+    out = {"A": a, "batch": batch, "policy": "logits ~ N(0, 0.25^2), one vector per epoch (graph and weights are constant "
+                                             "inside sample_states, gflownet.py:164-172)"}
+
+    def ev_time(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms)), r
+
+    ms_t, (taken, length) = ev_time(lambda: ctx.sample_taken(logits, batch, 12345, 0))
+    ids = int(length.sum())
+    ld = int(length.max())
+    ms_o, acts = ev_time(lambda: ctx.sample_order(logits, length, 12345, 0, dtype=torch.int32, ld=ld))
+    ms_r, _ = ev_time(lambda: ctx.reward_from_taken(taken, 0.5, "copy", torch.float32))
+    # spot check inside the run: one row's order against a device-side sort of the exported keys
+    _, l1, k1 = ctx.sample_taken(logits, 1, 12345, 0, export_keys=True)
+    sel = torch.nonzero(k1[0, : a - 1] < 0).squeeze(1)
+    want = sel[torch.sort(k1[0, sel], stable=True).indices]
+    ok = bool(torch.equal(acts[0, : int(l1[0]) - 1].long(), want)) and int(acts[0, int(l1[0]) - 1]) == a - 1
+    out["whole_trajectory(K4g)"] = {
+        "taken_ms": ms_t, "order_ms": ms_o, "trajectories_per_s": batch / ((ms_t + ms_o) / 1e3),
+        "trajectories_per_s_mask_only": batch / (ms_t / 1e3), "ids_drawn_per_step": ids, "max_length": ld,
+        "ids_ordered_per_s": ids / (ms_o / 1e3), "keys_generated_per_s": 1.0 * batch * a / (ms_t / 1e3),
+        "actions_bytes": int(acts.numel()) * 4, "order_check_row0": ok,
+        "sample_plus_reward_ms": ms_t + ms_r, "reward_from_taken_ms": ms_r,
+        "sample_plus_reward_patterns_per_s": batch / ((ms_t + ms_r) / 1e3)}
+    del acts
+    # K4: one masked categorical step for every sample (three passes over the A logits per sample)
+    words = (a + 31) // 32
+    tk = torch.zeros((batch, words), dtype=torch.int32, device=dev)
+    done = torch.zeros(batch, dtype=torch.uint8, device=dev)
+    act = torch.empty(batch, dtype=torch.int64, device=dev)
+    pr = torch.empty(batch, dtype=torch.float32, device=dev)
+    u = torch.rand(batch, generator=g, device=dev)
+    ms_s, _ = ev_time(lambda: ctx.sample_step(logits, tk, u, done, act, pr), reps=5)
+    out["single_step(K4)"] = {"ms_per_step": ms_s, "sample_steps_per_s": batch / (ms_s / 1e3),
+                              "logit_bytes_read_per_step": 3.0 * batch * a * 4,
+                              "gbps_on_logit_reads(L2)": 3.0 * batch * a * 4 / ms_s / 1e6,
+                              "note": "a whole trajectory needs T ~ A/2 of these: use the whole-trajectory kernels"}
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -863,6 +923,14 @@ def run_b200_arm(args):
                "sample": f"{args.cpu_sample} trajectories of the same workload, copy/fp32, numpy/scipy oracle "
                          f"single process ({dt:.1f} s); `--impl reference` runs the same port on all host cores"}
 
+    sampler_res = None
+    if rank == 0 and world == 1 and not args.no_extras and not args.no_sampler:
+        try:
+            sampler_res = sampler_bench(ctx, p, dev, B, flush)
+        except Exception as exc:        # report, never hide
+            sampler_res = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
     info = ctx.info()
     ctx_bytes = int(info.device_bytes)
     contributions, max_union = int(info.contributions), int(info.max_row_union)
@@ -902,6 +970,7 @@ def run_b200_arm(args):
             "cpu_baseline": cpu,
             "parity_check": parity,
             "extras": extras,
+            "sampler": sampler_res,
             "configs": configs,
             "context": {"setup_s": setup_s, "plan_contributions": contributions,
                         "device_bytes": ctx_bytes, "max_row_union": max_union,

@@ -259,6 +259,33 @@ class SpaiContext:
                                             _ptr(length), self._stream()), "spai_pack_taken_dev")
         return taken, length
 
+    def sample_taken(self, logits: torch.Tensor, bsz: int, seed: int, sample0: int = 0, export_keys: bool = False):
+        """Whole trajectories by the exponential race (K4g, spai_sample_taken_dev): logits f32[A] (CUDA) ->
+        (taken int32[B, words], length int32[B]) and, with export_keys (tests), the keys f32[B, A]."""
+        a = logits.numel()
+        words = (a + 31) // 32
+        dev = logits.device
+        taken = torch.empty((bsz, words), dtype=torch.int32, device=dev)
+        length = torch.empty(bsz, dtype=torch.int32, device=dev)
+        keys = torch.empty((bsz, a), dtype=torch.float32, device=dev) if export_keys else None
+        check(self._lib.spai_sample_taken_dev(self.device, _ptr(logits), a, bsz, int(seed) & (2 ** 64 - 1), int(sample0),
+                                              _ptr(taken), words, _ptr(length), _ptr(keys) if export_keys else None,
+                                              a if export_keys else 0, self._stream()), "spai_sample_taken_dev")
+        return (taken, length, keys) if export_keys else (taken, length)
+
+    def sample_order(self, logits: torch.Tensor, length: torch.Tensor, seed: int, sample0: int = 0,
+                     dtype: torch.dtype = torch.int32, ld: int = 0) -> torch.Tensor:
+        """The drawn ids in draw order (K4g, spai_sample_order_dev): int32/int64 [B, ld] with the terminal id last
+        and -1 padding; `length` from sample_taken with the same logits / seed / sample0."""
+        bsz = length.numel()
+        if ld <= 0:
+            ld = int(length.max()) if bsz else 1
+        out = torch.empty((bsz, ld), dtype=dtype, device=logits.device)
+        check(self._lib.spai_sample_order_dev(self.device, _ptr(logits), logits.numel(), bsz, int(seed) & (2 ** 64 - 1),
+                                              int(sample0), _ptr(length), _ptr(out), out.element_size(), ld,
+                                              self._stream()), "spai_sample_order_dev")
+        return out
+
     def sample_step(self, logits, taken, uniforms, done, action, prob):
         """In-place masked categorical step on CUDA tensors (include/spai_b200.h)."""
         a = logits.shape[-1]

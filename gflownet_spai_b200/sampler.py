@@ -201,37 +201,19 @@ class GFlowNet(nn.Module):
         out = pa / torch.where(valid, den, torch.ones_like(den)).clamp_min(1e-300)
         return torch.where(valid, out, torch.ones_like(out)).to(p.dtype)
 
-    def _sample_gumbel(self, logits, bsz, dev, generator, chunk_bytes=2 << 30):
-        """Whole trajectories at once (Gumbel-top-k): ids sorted by logit + Gumbel
-        noise, cut at the terminal id — equal in distribution to drawing one id per
-        step from the re-normalised untaken mass (Plackett-Luce), but O(A log A) per
-        sample instead of O(A * T). Returns (actions [B, T] with -1 padding,
-        taken int32 [B, words])."""
+    def _sample_gumbel(self, logits, bsz, dev, generator, sample0: int = 0, id_dtype=torch.int64):
+        """Whole trajectories at once (exponential race / Gumbel-top-k, kernels K4g): equal in
+        distribution to drawing one id per step from the re-normalised untaken mass (Plackett-Luce),
+        O(A) per sample instead of O(A * T). The keys are a pure function of (seed, sample index, id)
+        (Philox, generated inside the kernels): no B x A tensor, no library sort. Returns
+        (actions [B, T] with the terminal last and -1 padding, taken int32 [B, words], length int32 [B])."""
         ctx = self.env.ctx
-        a = logits.numel()
-        chunk = max(1, min(bsz, int(chunk_bytes // (4 * a))))
-        acts, takens = [], []
-        for b0 in range(0, bsz, chunk):
-            c = min(chunk, bsz - b0)
-            u = torch.rand((c, a), device=dev, generator=generator).clamp_(1e-20, 1.0 - 1e-7)
-            keys = logits[None, :] - torch.log(-torch.log(u))
-            del u
-            taken, length = ctx.pack_taken(keys)
-            lmax = int(length.max())
-            term = keys[:, a - 1:a].clone()
-            keys[:, a - 1] = float("inf")                          # terminal sorts first, moved last below
-            order = torch.topk(keys, lmax, dim=1, sorted=True).indices    # [c, lmax], terminal in column 0
-            drawn = torch.roll(order, shifts=-1, dims=1)           # terminal to the end of the full-length rows
-            pos = torch.arange(lmax, device=dev)[None, :]
-            ln = length.to(torch.int64)[:, None]
-            out = torch.where(pos < ln - 1, drawn, torch.full_like(drawn, -1))
-            out.scatter_(1, ln - 1, torch.full((c, 1), a - 1, dtype=torch.int64, device=dev))
-            acts.append(out)
-            takens.append(taken)
-            del keys, order, drawn, term
-        tmax = max(x.shape[1] for x in acts)
-        acts = [torch.nn.functional.pad(x, (0, tmax - x.shape[1]), value=-1) for x in acts]
-        return torch.cat(acts, dim=0), torch.cat(takens, dim=0)
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator,
+                                 device=generator.device if generator is not None else "cpu"))
+        self.last_seed = seed
+        taken, length = ctx.sample_taken(logits, bsz, seed, sample0)
+        actions = ctx.sample_order(logits, length, seed, sample0, dtype=id_dtype)
+        return actions, taken, length
 
     def sample_states(self, s0, return_log=False, generator: torch.Generator | None = None,
                       method: str = "step"):
@@ -252,7 +234,9 @@ class GFlowNet(nn.Module):
         taken = torch.zeros((bsz, words), dtype=torch.int32, device=dev)
         done = torch.zeros(bsz, dtype=torch.uint8, device=dev)
         if method == "gumbel":
-            complete_actions, taken = self._sample_gumbel(logits, bsz, dev, generator)
+            if not bool(torch.isfinite(logits).all()):
+                raise RuntimeError("sample_states: the forward policy returned non-finite probabilities")
+            complete_actions, taken, _ = self._sample_gumbel(logits, bsz, dev, generator)
             al = float(alpha.detach()) if isinstance(alpha, torch.Tensor) else float(alpha)
             rewards = self.env.update_from_taken(taken, al, max_deletions=complete_actions.shape[1])["reward"]
             if log is not None:

@@ -221,6 +221,30 @@ int spai_finalize_rewards_dev(spai_ctx* ctx, const double* res2_dev, const int64
 int spai_pack_taken_dev(spai_ctx* ctx, const float* keys_dev, int64_t keys_ld, int64_t A, int64_t B,
                         uint32_t* taken_dev, int64_t words_ld, int32_t* length_dev, void* stream);
 
+/* ---- Whole trajectories of the environment step on the device. ----
+ * gflownet/gflownet.py:135-179 draws one id per step from the masked, re-normalised policy
+ * (policy.py:64-73) until the terminal id A-1 comes up. With one logits vector per epoch that
+ * process is an exponential race (id i arrives at E_i / exp(logit_i), E_i ~ Exp(1)): ids come out
+ * in order of arrival and the trajectory ends at the terminal's arrival — the same distribution,
+ * O(A) per sample instead of O(A * T). E_i = Philox4x32-10(key = seed, counter = (i / 4, sample0 + b)),
+ * so a key depends on (seed, global sample index, id) only: no B x A tensor exists at any point and a
+ * shard [sample0, sample0 + B) of a batch equals the same rows of the full batch.
+ *
+ * spai_sample_taken_dev: taken_dev u32[B, words_ld] = bitmask of the ids drawn before the terminal
+ *   plus the terminal's bit (the input of spai_reward_from_taken_dev), length_dev i32[B] = ids drawn,
+ *   terminal included. keys_out_dev (tests; may be NULL) f32[B, keys_ld] receives every key
+ *   lq = log(t_i / t_terminal) (0 for the terminal): id i is drawn iff lq < 0, in ascending (lq, id) order.
+ * spai_sample_order_dev: actions_dev (id_bytes 4: i32, 8: i64) [B, ld] = the drawn ids in draw order,
+ *   the terminal id last, then -1 padding (the layout of Log._actions transposed, log.py:89); length_dev
+ *   from spai_sample_taken_dev with the same logits / seed / sample0; ld >= max length. Synchronises
+ *   `stream` (a trajectory longer than ld is SPAI_ERR_INVALID). */
+int spai_sample_taken_dev(int device, const float* logits_dev, int64_t A, int64_t B, uint64_t seed,
+                          int64_t sample0, uint32_t* taken_dev, int64_t words_ld, int32_t* length_dev,
+                          float* keys_out_dev, int64_t keys_ld, void* stream);
+int spai_sample_order_dev(int device, const float* logits_dev, int64_t A, int64_t B, uint64_t seed,
+                          int64_t sample0, const int32_t* length_dev, void* actions_dev, int id_bytes,
+                          int64_t ld, void* stream);
+
 /* ---- Device-side ingest: the step immediately before the reward path. ----
  * All array arguments are DEVICE pointers on `device`; outputs are caller-allocated; totals that
  * size a later allocation come back through a HOST pointer (the call synchronises `stream`).

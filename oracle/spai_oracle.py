@@ -31,7 +31,7 @@ __all__ = [
     "matrix_flops", "evaluate_preconditioner", "reward_from_residual",
     "baseline_constants", "reward_batch_copy", "row_index_sets",
     "ls_row_residual2", "residual_ls", "reward_batch_ls", "masked_softmax_probs",
-    "sample_step",
+    "sample_step", "philox4x32_10", "race_keys", "race_trajectory",
 ]
 
 
@@ -272,3 +272,55 @@ def sample_step(logits: np.ndarray, taken_lists, uniforms, done):
         prob[b] = np.float32(p[idx] / cdf[-1])
         done_out[b] = idx == a - 1
     return act, prob, done_out
+
+
+# --------------------------------------------------------------------------
+# whole trajectories by the exponential race (K4g)
+# --------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11;
+    the Random123 reference implementation, the generator behind torch.cuda / curand). Not in the
+    reference repository (it draws with torch.multinomial, gflownet.py:148, whose stream cannot be
+    reproduced); this is the published algorithm, pinned by the Random123 known-answer vectors in
+    tests/test_oracle.py. counter uint32[..., 4], key uint32[..., 2] -> uint32[..., 4]."""
+    c = np.array(counter, dtype=np.uint64, copy=True)
+    k = np.array(np.broadcast_to(np.asarray(key, dtype=np.uint64), c.shape[:-1] + (2,)), copy=True)
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[..., 0], m1 * c[..., 2]
+        c = np.stack([(p1 >> np.uint64(32)) ^ c[..., 1] ^ k[..., 0], p1 & mask,
+                      (p0 >> np.uint64(32)) ^ c[..., 3] ^ k[..., 1], p0 & mask], axis=-1)
+        k = np.stack([(k[..., 0] + np.uint64(0x9E3779B9)) & mask, (k[..., 1] + np.uint64(0xBB67AE85)) & mask], axis=-1)
+    return c.astype(np.uint32)
+
+
+def race_keys(logits, seed: int, sample: int) -> np.ndarray:
+    """Keys of the exponential race that is equal in distribution to the reference's step loop
+    (gflownet.py:135-179 with the masked softmax of policy.py:64-73; Plackett-Luce / Gumbel-top-k):
+    id i arrives at t_i = E_i / exp(logit_i); lq_i = log(t_i / t_terminal) in float64 (0 for the terminal
+    id A-1). E_i = -log(u_i), u_i = (x_i + 1/2) / 2^32, x_i = word (i mod 4) of
+    Philox4x32-10(counter = (i // 4, sample), key = seed)."""
+    lg = np.asarray(logits, dtype=np.float64)
+    a = lg.shape[0]
+    groups = (a + 3) // 4
+    g = np.arange(groups, dtype=np.uint64)
+    ctr = np.stack([g & np.uint64(0xFFFFFFFF), g >> np.uint64(32),
+                    np.full(groups, sample & 0xFFFFFFFF, dtype=np.uint64),
+                    np.full(groups, (sample >> 32) & 0xFFFFFFFF, dtype=np.uint64)], axis=-1)
+    x = philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint64)).reshape(-1)[:a]
+    xf = x.astype(np.float64)
+    upper = x >= np.uint32(0x80000000)
+    e = np.where(upper, -np.log1p(-((4294967295.0 - xf) + 0.5) / 4294967296.0), -np.log((xf + 0.5) / 4294967296.0))
+    arr = np.log(e) - lg
+    lq = arr - arr[a - 1]
+    lq[a - 1] = 0.0
+    return lq
+
+
+def race_trajectory(lq: np.ndarray) -> np.ndarray:
+    """The trajectory the keys define: ids with lq < 0 in ascending (lq, id) order, then the terminal id."""
+    lq = np.asarray(lq)
+    a = lq.shape[0]
+    ids = np.nonzero(lq[: a - 1] < 0)[0]
+    order = ids[np.lexsort((ids, lq[ids]))]
+    return np.concatenate([order, [a - 1]]).astype(np.int64)

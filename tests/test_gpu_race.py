@@ -1,0 +1,157 @@
+"""K4g: whole trajectories by the exponential race (spai_sample_taken_dev / spai_sample_order_dev)
+against the oracle's restatement (Philox4x32-10 known answers + float64 keys) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from gflownet_spai_b200 import synth
+from oracle import spai_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gflownet_spai_b200.env import SpaiContext
+    p = synth.make_problem("cfg1")
+    coo = p.a.tocoo()
+    c = SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data, device=0)
+    yield c
+    c.close()
+
+
+def _unpack(taken, a):
+    t = taken.cpu().numpy().view(np.uint32)
+    bits = ((t[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(t.shape[0], -1)[:, :a]
+    return bits.astype(bool)
+
+
+def _check_against_keys(keys, taken, length, acts, a):
+    """Everything the kernels emit must follow from the keys THEY computed: taken = {lq < 0} + terminal,
+    order = ascending (lq, id), terminal last, -1 padding."""
+    keys = keys.cpu().numpy()
+    bits = _unpack(taken, a)
+    ln = length.cpu().numpy()
+    acts = acts.cpu().numpy()
+    for b in range(keys.shape[0]):
+        want = orc.race_trajectory(keys[b])
+        assert ln[b] == want.size
+        wbits = np.zeros(a, dtype=bool)
+        wbits[want] = True
+        assert np.array_equal(bits[b], wbits)
+        assert np.array_equal(acts[b, :ln[b]], want)
+        assert np.all(acts[b, ln[b]:] == -1)
+
+
+@pytest.mark.parametrize("a,scale", [(2, 1.0), (5, 1.0), (461, 2.0), (4099, 0.5), (70001, 3.0)])
+@pytest.mark.parametrize("id_dtype", [torch.int32, torch.int64])
+def test_race_keys_match_oracle_and_outputs_follow_keys(ctx, a, scale, id_dtype):
+    rng = np.random.default_rng(a)
+    logits = (rng.normal(size=a) * scale).astype(np.float32)
+    lg = torch.from_numpy(logits).cuda()
+    bsz, seed, s0 = 12, 0x1234_5678_9ABC_DEF0 + a, 7
+    taken, length, keys = ctx.sample_taken(lg, bsz, seed, s0, export_keys=True)
+    acts = ctx.sample_order(lg, length, seed, s0, dtype=id_dtype)
+    assert acts.dtype == id_dtype and acts.shape[1] == int(length.max())
+    _check_against_keys(keys, taken, length, acts, a)
+    # the keys themselves: Philox bits exact, fp32 transform vs float64 restatement
+    k = keys.cpu().numpy()
+    for b in (0, bsz - 1):
+        want = orc.race_keys(logits, seed, s0 + b)
+        np.testing.assert_allclose(k[b], want, rtol=2e-5, atol=2e-5)
+    # sharding: rows [5, 9) drawn as their own call equal the same rows of the batch
+    t2, l2 = ctx.sample_taken(lg, 4, seed, s0 + 5)
+    assert torch.equal(t2, taken[5:9]) and torch.equal(l2, length[5:9])
+    a2 = ctx.sample_order(lg, l2, seed, s0 + 5, dtype=id_dtype, ld=acts.shape[1])
+    assert torch.equal(a2, acts[5:9])
+
+
+@pytest.mark.parametrize("kind", ["peaked", "terminal_unlikely", "terminal_certain", "flat", "two_level"])
+def test_race_orders_exactly_for_skewed_policies(ctx, kind):
+    """Bucket occupancy depends on the policy; the order must not: heavy hitters, a terminal that
+    almost never / almost always comes first, equal logits (ties broken by id), 60-nat spread."""
+    a = 20011
+    rng = np.random.default_rng(3)
+    lg = np.zeros(a, dtype=np.float32)
+    if kind == "peaked":
+        lg[:] = rng.normal(size=a) * 0.1
+        lg[rng.choice(a - 1, 50, replace=False)] += 12.0
+    elif kind == "terminal_unlikely":
+        lg[-1] = -60.0
+    elif kind == "terminal_certain":
+        lg[-1] = 30.0
+    elif kind == "two_level":
+        lg[: a // 2] = -40.0
+        lg[-1] = -45.0
+    t = torch.from_numpy(lg).cuda()
+    taken, length, keys = ctx.sample_taken(t, 6, 99, 0, export_keys=True)
+    acts = ctx.sample_order(t, length, 99, 0)
+    _check_against_keys(keys, taken, length, acts, a)
+    if kind == "terminal_unlikely":
+        assert int(length.min()) == a            # every id is drawn before the terminal
+    if kind == "terminal_certain":
+        assert int(length.max()) <= 3
+
+
+def test_race_distribution_matches_the_step_process(ctx):
+    """Plackett-Luce equivalence, measured: first id ~ softmax(logits); second given the first
+    ~ p_j / (1 - p_i); P(length = 1) = p_terminal."""
+    a = 40
+    rng = np.random.default_rng(5)
+    logits = rng.normal(size=a).astype(np.float32)
+    logits[-1] += 1.0
+    p = np.exp(logits.astype(np.float64))
+    p /= p.sum()
+    bsz = 200000
+    t = torch.from_numpy(logits).cuda()
+    taken, length = ctx.sample_taken(t, bsz, 2024, 0)
+    acts = ctx.sample_order(t, length, 2024, 0).cpu().numpy()
+    first = acts[:, 0]
+    counts = np.bincount(first, minlength=a).astype(np.float64)
+    chi2 = float(((counts - bsz * p) ** 2 / (bsz * p)).sum())
+    assert chi2 < 84.0                                            # chi2(39 dof) 99.997th percentile
+    i = int(np.argmax(p[:-1]))
+    sel = acts[first == i]
+    c2 = np.bincount(sel[:, 1], minlength=a).astype(np.float64)
+    e2 = sel.shape[0] * p / (1 - p[i])
+    e2[i] = 0
+    keep = e2 > 0
+    assert c2[i] == 0
+    assert float(((c2[keep] - e2[keep]) ** 2 / e2[keep]).sum()) < 82.0
+    frac = float((length.cpu().numpy() == 1).mean())
+    assert abs(frac - p[-1]) < 5 * np.sqrt(p[-1] * (1 - p[-1]) / bsz)
+
+
+@pytest.mark.parametrize("a", [524281, 8372225])
+def test_race_full_size_order_and_mask(ctx, a):
+    """cfg2 / cfg4 action counts (K4 was only tested to A = 4099): the order the kernel
+    writes equals a device-side stable sort of its own exported keys; mask and length agree."""
+    g = torch.Generator(device="cuda").manual_seed(a)
+    lg = torch.randn(a, generator=g, device="cuda") * 0.3
+    bsz = 3
+    taken, length, keys = ctx.sample_taken(lg, bsz, 77, 1000, export_keys=True)
+    acts = ctx.sample_order(lg, length, 77, 1000)
+    for b in range(bsz):
+        k = keys[b, : a - 1]
+        ids = torch.nonzero(k < 0).squeeze(1)
+        order = ids[torch.sort(k[ids], stable=True).indices]       # ids ascending -> stable sort == (lq, id) order
+        n = int(length[b])
+        assert n == ids.numel() + 1
+        assert torch.equal(acts[b, : n - 1].long(), order)
+        assert int(acts[b, n - 1]) == a - 1 and bool((acts[b, n:] == -1).all())
+    bits = torch.zeros((bsz, taken.shape[1] * 32), dtype=torch.bool, device="cuda")
+    t64 = taken.long() & 0xFFFFFFFF
+    for j in range(32):
+        bits[:, j::32] = ((t64 >> j) & 1).bool()
+    want = keys < 0
+    want[:, a - 1] = True
+    assert torch.equal(bits[:, :a], want)
+
+
+def test_order_rejects_short_ld_and_foreign_lengths(ctx):
+    lg = torch.zeros(1000, device="cuda")
+    taken, length = ctx.sample_taken(lg, 8, 1, 0)
+    with pytest.raises(ValueError):
+        ctx.sample_order(lg, length, 1, 0, ld=max(1, int(length.max()) - 1))
+    with pytest.raises(ValueError):
+        ctx.sample_order(lg, length, 2, 0)          # lengths of another seed

@@ -100,3 +100,27 @@ def test_sample_step_known_answers():
     assert prob[3] == 1.0
     assert prob[1] == pytest.approx(0.5, rel=1e-5)          # 0.3 / (0.1+0.2+0.3)
     assert prob[2] == pytest.approx(4.0 / 7.0, rel=1e-5)
+
+
+def test_philox_known_answers_and_race_oracle():
+    """Philox4x32-10 against the Random123 known-answer vectors (kat_vectors of the reference
+    implementation), then the race oracle's invariants."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = orc.philox4x32_10(np.array(c, dtype=np.uint64), np.array(k, dtype=np.uint64))
+        assert tuple(int(v) for v in got) == want
+    lg = np.random.default_rng(0).normal(size=301)
+    lq = orc.race_keys(lg, seed=9, sample=4)
+    tr = orc.race_trajectory(lq)
+    assert tr[-1] == 300 and len(set(tr.tolist())) == tr.size and lq[300] == 0.0
+    assert np.all(np.diff(lq[tr[:-1]]) >= 0) and np.all(lq[tr[:-1]] < 0)
+    assert not np.array_equal(lq, orc.race_keys(lg, seed=9, sample=5))
+    # first arrival ~ softmax (exponential race), 20000 samples, 5 categories
+    lg5 = np.array([0.0, 1.0, -1.0, 0.5, 0.2])
+    p = np.exp(lg5) / np.exp(lg5).sum()
+    first = np.array([int(np.argmin(orc.race_keys(lg5, 1, s))) for s in range(20000)])
+    cnt = np.bincount(first, minlength=5)
+    assert float(((cnt - 20000 * p) ** 2 / (20000 * p)).sum()) < 23.5        # chi2(4 dof) 99.99th percentile
