@@ -637,6 +637,28 @@ def sampler_bench(ctx, p, dev, batch, flush):
                               "logit_bytes_read_per_step": 3.0 * batch * a * 4,
                               "gbps_on_logit_reads(L2)": 3.0 * batch * a * 4 / ms_s / 1e6,
                               "note": "a whole trajectory needs T ~ A/2 of these: use the whole-trajectory kernels"}
+    # K4p: the same step with running block sums, whole trajectories in ONE launch (a warp per sample)
+    try:
+        bp = min(batch, 1024)
+        tk2 = torch.zeros((bp, words), dtype=torch.int32, device=dev)
+        dn2 = torch.zeros(bp, dtype=torch.uint8, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.sample_steps(logits, torch.zeros((8, words), dtype=torch.int32, device=dev),
+                         torch.zeros(8, dtype=torch.uint8, device=dev), 64, seed=1)          # warm-up (module load)
+        torch.cuda.synchronize()
+        e0.record()
+        acts2, _, steps2 = ctx.sample_steps(logits, tk2, dn2, a, seed=777, want_probs=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_p = e0.elapsed_time(e1)
+        nst = int(steps2.sum())
+        out["multi_step(K4p)"] = {"batch": bp, "ms": ms_p, "steps_drawn": nst, "sample_steps_per_s": nst / (ms_p / 1e3),
+                                  "trajectories_per_s": bp / (ms_p / 1e3), "all_done": bool(dn2.all()),
+                                  "longest_trajectory": int(steps2.max()),
+                                  "speedup_per_step_vs_K4": (nst / (ms_p / 1e3)) / (batch / (ms_s / 1e3))}
+        del acts2
+    except Exception as exc:
+        out["multi_step(K4p)"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 

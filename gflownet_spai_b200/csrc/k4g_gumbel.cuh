@@ -18,10 +18,11 @@
 //                    lq into NB <= 32768 buckets whose EXPECTED occupancy is equal (histogram in shared
 //                    memory -> scan -> scatter (key, id) to an L2-resident scratch row), then finish
 //                    each bucket by rank counting, one thread pair per bucket on shared-memory tiles.
-//                    The map is piecewise linear between quantiles of the expected-arrivals function
-//                    N(t) = sum_i (1 - exp(-w_i t)) of THIS policy (k4g_ntable_kernel), monotone by
-//                    construction (fmaf of a non-negative slope, clamped to the segment's ends), so
-//                    bucket order == key order exactly and occupancy stays ~uniform for any policy.
+//                    The map is the expected-arrivals function N(t) = sum_i (1 - exp(-w_i t)) of THIS policy
+//                    (k4g_ntable_kernel) tabulated per sample on 4096 cells uniform in lq, piecewise linear
+//                    and monotone by construction (max-scanned table, fmaf of a non-negative difference,
+//                    clamped to the cell's ends), so bucket order == key order exactly and occupancy stays
+//                    ~uniform for any policy.
 #pragma once
 
 #include "spai_internal.cuh"
@@ -31,20 +32,18 @@ namespace spai {
 constexpr int K4G_TABLE = 832;                 // log2 t in [-40, 168), 4 points per octave
 constexpr float K4G_LOG2T_MIN = -40.f;
 constexpr float K4G_PER_OCTAVE = 4.f;
-constexpr int K4G_FINE = 16;                   // geometric refinement below the first quantile
-constexpr int K4G_QUANT = 256;
-constexpr int K4G_BND = 1 + K4G_FINE + K4G_QUANT;   // 273 boundaries, 272 segments
-constexpr int K4G_BND_PAD = 276;               // array stride (keeps the 8-byte tile aligned)
+constexpr int K4G_CELLS = 4096;                // cells of the per-sample bucket map, uniform in lq over [-K4G_LQ_SPAN, 0)
+constexpr float K4G_LQ_SPAN = 24.f;            // exp(-24) = 4e-11 of the terminal's arrival time: everything earlier -> bucket 0
 constexpr int K4G_COUNT_THREADS = 512;
 constexpr int K4G_THREADS = 1024;
 constexpr int K4G_TILE_BUCKETS = K4G_THREADS / 2;   // one thread pair per bucket
-constexpr int K4G_TILE_CAP = 10240;            // (key, id) pairs of a tile in shared memory (80 KB)
+constexpr int K4G_TILE_CAP = 8192;             // (key, id) pairs of a tile in shared memory (64 KB)
 constexpr int K4G_BIG = 128;                   // buckets above this are ranked by the whole CTA
 constexpr int K4G_BIG_LIST = 128;
 constexpr int K4G_MAX_BUCKETS = 32768;
 
 __host__ __device__ constexpr int k4g_smem_bytes(int nb) {
-  return nb * 4 + K4G_BND_PAD * 12 + 256 + K4G_BIG_LIST * 4 + K4G_TILE_CAP * 8;
+  return nb * 4 + (K4G_CELLS + 4) * 4 + 256 + K4G_BIG_LIST * 4 + K4G_TILE_CAP * 8;
 }
 
 // Philox4x32-10 (Salmon et al., SC'11): round keys key + r * (0x9E3779B9, 0xBB67AE85)
@@ -60,13 +59,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// log of an Exp(1) variate from 32 random bits, accurate at both ends: u = (x + 1/2) / 2^32,
-// E = -log u for u < 1/2, E = -log1p(-(1 - u)) above (where 1 - u is exact in fp32 and u is not).
+// log of an Exp(1) variate from 32 random bits: u = (x + 1/2) / 2^32, E = -log u. Relative error of E
+// <= 6e-6 everywhere, also for u -> 1 where E -> 0 (the earliest arrivals): there 1 - u = d is what fp32
+// holds exactly, E = -log(1 - d) = d + d^2/2 + ... (degree 6 below d = 1/16, truncation 2^-27 relative),
+// and one MUFU.LG2 serves both other ranges (its 2^-21.4 absolute error is relative to E >= 0.0645).
+// Branch-free: the warp never runs two log paths back to back.
 __device__ __forceinline__ float k4g_log_exp1(uint32_t x) {
-  float e;
-  if (x & 0x80000000u) e = -log1pf(-(((float)(~x) + 0.5f) * 2.3283064365386963e-10f));
-  else e = -logf(((float)x + 0.5f) * 2.3283064365386963e-10f);
-  return logf(e);
+  const bool top = (x & 0x80000000u) != 0u;
+  const float d = ((float)(~x) + 0.5f) * 2.3283064365386963e-10f;      // 1 - u
+  const float u = ((float)x + 0.5f) * 2.3283064365386963e-10f;
+  float e = -__logf(top ? 1.0f - d : u);
+  const float poly = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, fmaf(d, 1.f / 6.f, 0.2f), 0.25f), 1.f / 3.f), 0.5f), 1.0f);
+  if (top && d < 0.0625f) e = poly;
+  return __logf(e);
 }
 
 __device__ __forceinline__ uint4 k4g_bits(int64_t group, int64_t sample, uint64_t seed) {
@@ -195,34 +200,16 @@ __device__ __forceinline__ float k4g_n_at(const float* __restrict__ ntab, float 
   const float f = x - (float)k;
   return ntab[k] + f * (ntab[k + 1] - ntab[k]);
 }
-// log2 t at which N reaches `target` (inverse of the same interpolant)
-__device__ __forceinline__ float k4g_lt_of(const float* __restrict__ ntab, float target) {
-  if (!(target > ntab[0])) return K4G_LOG2T_MIN + log2f(fmaxf(target, 1e-38f) / fmaxf(ntab[0], 1e-38f));
-  int lo = 0, hi = K4G_TABLE - 1;                 // ntab[lo] < target <= ntab[hi] (or the end of the grid)
-  if (target > ntab[hi]) return K4G_LOG2T_MIN + (float)hi / K4G_PER_OCTAVE;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (ntab[mid] < target) lo = mid; else hi = mid;
-  }
-  const float d = ntab[hi] - ntab[lo];
-  const float f = d > 0.f ? (target - ntab[lo]) / d : 0.f;
-  return K4G_LOG2T_MIN + ((float)lo + f) / K4G_PER_OCTAVE;
-}
-
 struct K4gMap {
-  const float* lqb;      // [K4G_BND] segment boundaries in lq (non-decreasing, last = 0)
-  const float* vb;       // [K4G_BND] bucket coordinate at the boundaries (non-decreasing)
-  const float* slope;    // [K4G_BND - 1] >= 0
+  const float* vb;       // [K4G_CELLS + 1] bucket coordinate at the cell boundaries (non-decreasing, vb[CELLS] = nb)
   int nb;
-  __device__ __forceinline__ int bucket(float lq) const {
-    int lo = 0, hi = K4G_BND - 1;                 // largest j with lqb[j] <= lq
-#pragma unroll
-    for (int it = 0; it < 9; ++it) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (lqb[mid] <= lq) lo = mid; else hi = mid - 1;
-    }
-    if (lo >= K4G_BND - 1) lo = K4G_BND - 2;
-    const float v = fminf(fmaf(slope[lo], lq - lqb[lo], vb[lo]), vb[lo + 1]);
+  __device__ __forceinline__ int bucket(float lq) const {          // lq < 0
+    const float x = (lq + K4G_LQ_SPAN) * ((float)K4G_CELLS / K4G_LQ_SPAN);
+    if (!(x > 0.f)) return 0;
+    int c = (int)x;
+    c = c < K4G_CELLS ? c : K4G_CELLS - 1;                          // x == CELLS only by rounding of lq -> -0
+    const float v0 = vb[c], v1 = vb[c + 1];
+    const float v = fminf(fmaf(v1 - v0, x - (float)c, v0), v1);     // monotone in lq inside the cell and across cells
     const int bk = (int)v;
     return bk < nb ? bk : nb - 1;
   }
@@ -241,10 +228,8 @@ k4g_order_kernel(const float* __restrict__ logits, int64_t A, uint64_t seed, int
                  OutT* __restrict__ actions, int64_t ld, int* __restrict__ work, int* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char k4g_smem[];
   uint32_t* off = reinterpret_cast<uint32_t*>(k4g_smem);
-  float* lqb = reinterpret_cast<float*>(off + nb);
-  float* vb = lqb + K4G_BND_PAD;
-  float* slope = vb + K4G_BND_PAD;
-  uint32_t* misc = reinterpret_cast<uint32_t*>(slope + K4G_BND_PAD);         // 64 words: scan partials, counters
+  float* vb = reinterpret_cast<float*>(off + nb);                        // [K4G_CELLS + 1] (+3 pad)
+  uint32_t* misc = reinterpret_cast<uint32_t*>(vb + K4G_CELLS + 4);      // 64 words: scan partials, counters
   uint32_t* big = misc + 64;
   unsigned long long* tile = reinterpret_cast<unsigned long long*>(big + K4G_BIG_LIST);
 
@@ -253,7 +238,7 @@ k4g_order_kernel(const float* __restrict__ logits, int64_t A, uint64_t seed, int
   const int64_t groups = (A + 3) >> 2;
   unsigned long long* my = scratch + (int64_t)blockIdx.x * scratch_ld;
   const float mx = mxp[0];
-  K4gMap map{lqb, vb, slope, nb};
+  K4gMap map{vb, nb};
 
   for (;;) {
     __syncthreads();
@@ -270,33 +255,38 @@ k4g_order_kernel(const float* __restrict__ logits, int64_t A, uint64_t seed, int
     }
     const float a_term = k4g_arrival(logits, A - 1, sample, seed);
 
-    // ---- per-sample map: boundaries at fixed fractions of the expected arrivals before t_terminal
+    // ---- per-sample map: vb[c] = nb * N(t at cell boundary c) / N(t_terminal), max-scanned
     for (int i = tid; i < nb; i += K4G_THREADS) off[i] = 0u;
-    if (tid < K4G_BND) {
+    {
       const float lt_term = (a_term + mx) * 1.4426950408889634f;
       const float n_term = k4g_n_at(ntab, lt_term);
-      float f;
-      if (tid == 0) f = 0.f;
-      else if (tid <= K4G_FINE) f = exp2f((float)(tid - 1 - K4G_FINE)) / (float)K4G_QUANT;
-      else f = (float)(tid - K4G_FINE) / (float)K4G_QUANT;
-      float q = -3.0e38f;
-      if (tid == K4G_BND - 1) q = 0.f;
-      else if (tid > 0 && n_term > 0.f && n_term < 3.0e38f)
-        q = fminf((k4g_lt_of(ntab, f * n_term) - lt_term) * 0.6931471805599453f, 0.f);
-      if (!(q == q)) q = 0.f;
-      lqb[tid] = q;
-      vb[tid] = f * (float)nb;
-    }
-    __syncthreads();
-    if (tid == 0) {                                                      // non-decreasing boundaries
-      float run = lqb[0];
-      for (int j = 1; j < K4G_BND; ++j) { run = fmaxf(run, lqb[j]); lqb[j] = run; }
-    }
-    __syncthreads();
-    if (tid < K4G_BND - 1) {
-      const float dq = lqb[tid + 1] - lqb[tid];
-      const float s = (tid > 0 && dq > 0.f) ? (vb[tid + 1] - vb[tid]) / dq : 0.f;
-      slope[tid] = (s == s && s < 3.0e38f) ? s : 0.f;
+      const float scale = (n_term > 0.f && n_term < 3.0e38f) ? (float)nb / n_term : 0.f;
+      float carry = 0.f;
+      for (int base = 0; base <= K4G_CELLS; base += K4G_THREADS) {
+        const int c = base + tid;
+        float v = 0.f;
+        if (c < K4G_CELLS) {
+          const float lqc = (float)c * (K4G_LQ_SPAN / (float)K4G_CELLS) - K4G_LQ_SPAN;
+          v = fminf(k4g_n_at(ntab, fmaf(lqc, 1.4426950408889634f, lt_term)) * scale, (float)nb);
+          if (!(v == v)) v = 0.f;
+        } else if (c == K4G_CELLS) v = (float)nb;
+        float inc = v;                                                   // inclusive max-scan with a carry
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) inc = fmaxf(inc, __shfl_up_sync(0xffffffffu, inc, o, 32) * (lane >= o ? 1.f : 0.f));
+        if (lane == 31) reinterpret_cast<float*>(misc)[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+          float w = reinterpret_cast<float*>(misc)[lane];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) w = fmaxf(w, __shfl_up_sync(0xffffffffu, w, o, 32) * (lane >= o ? 1.f : 0.f));
+          reinterpret_cast<float*>(misc)[lane] = w;
+        }
+        __syncthreads();
+        const float before = fmaxf(carry, warp ? reinterpret_cast<float*>(misc)[warp - 1] : 0.f);
+        if (c <= K4G_CELLS) vb[c] = fmaxf(before, inc);
+        carry = fmaxf(carry, reinterpret_cast<float*>(misc)[31]);
+        __syncthreads();
+      }
     }
     __syncthreads();
 

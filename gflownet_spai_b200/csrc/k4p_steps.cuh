@@ -39,11 +39,52 @@ struct K4pState {
   const float* lg;
   uint32_t* tk;
   float* S;
-  int64_t A;
-  int blk, per, nblk, c, lane;
+  int64_t A, words;
+  int blk, per, nblk, c, lane;       // per = ids per lane of a block (a multiple of 4)
+  bool vec_ok;
   float mx, C;
 
-  __device__ __forceinline__ bool untaken(int64_t id) const { return !((tk[id >> 5] >> (id & 31)) & 1u); }
+  // bit j = id0 + j is untaken and < A (cnt <= 32 ids)
+  __device__ __forceinline__ uint32_t untaken_bits(int64_t id0, int cnt) const {
+    const int64_t w = id0 >> 5;
+    const int sh = (int)(id0 & 31);
+    const uint32_t w0 = (w < words) ? tk[w] : 0xffffffffu;
+    const uint32_t w1 = (sh && w + 1 < words) ? tk[w + 1] : 0xffffffffu;
+    uint32_t bits = ~__funnelshift_r(w0, w1, sh);
+    if (cnt < 32) bits &= (1u << cnt) - 1u;
+    const int64_t room = A - id0;
+    if (room < 32) bits &= room <= 0 ? 0u : ((1u << (int)room) - 1u);
+    return bits;
+  }
+
+  // sum of exp(l - mx) over this lane's contiguous ids of the block starting at `base`: the mask words
+  // and the logits are loaded unconditionally (independent 16-byte loads in flight), then selected
+  __device__ __forceinline__ float lane_sum(int64_t base) const {
+    const int64_t lo = base + (int64_t)lane * per;
+    float s = 0.f;
+    for (int i0 = 0; i0 < per; i0 += 32) {
+      const int cnt = per - i0 < 32 ? per - i0 : 32;
+      const int64_t id0 = lo + i0;
+      const uint32_t bits = untaken_bits(id0, cnt);
+#pragma unroll 4
+      for (int j = 0; j < cnt; j += 4) {
+        float4 v;
+        if (vec_ok && id0 + j + 3 < A) v = *reinterpret_cast<const float4*>(lg + id0 + j);
+        else {
+          v.x = id0 + j < A ? lg[id0 + j] : 0.f;
+          v.y = id0 + j + 1 < A ? lg[id0 + j + 1] : 0.f;
+          v.z = id0 + j + 2 < A ? lg[id0 + j + 2] : 0.f;
+          v.w = id0 + j + 3 < A ? lg[id0 + j + 3] : 0.f;
+        }
+        const uint32_t nb = bits >> j;
+        s += (nb & 1u) ? __expf(v.x - mx) : 0.f;
+        s += (nb & 2u) ? __expf(v.y - mx) : 0.f;
+        s += (nb & 4u) ? __expf(v.z - mx) : 0.f;
+        s += (nb & 8u) ? __expf(v.w - mx) : 0.f;
+      }
+    }
+    return s;
+  }
 
   // max over the untaken logits, then every block sum and this lane's chunk sum
   __device__ void rebuild() {
@@ -65,17 +106,6 @@ struct K4pState {
     for (int j = 0; j < c; ++j) cs += S[lane * c + j];
     C = cs;
   }
-
-  // sum of exp(l - mx) over this lane's contiguous ids of the block starting at `base`
-  __device__ __forceinline__ float lane_sum(int64_t base) const {
-    const int64_t lo = base + (int64_t)lane * per;
-    float s = 0.f;
-    for (int i = 0; i < per; ++i) {
-      const int64_t id = lo + i;
-      if (id < A && untaken(id)) s += __expf(lg[id] - mx);
-    }
-    return s;
-  }
 };
 
 template <typename OutT>
@@ -94,7 +124,9 @@ k4p_steps_kernel(const float* __restrict__ logits, int64_t A, uint32_t* __restri
   if (!done[b]) {
     K4pState st;
     st.lg = logits; st.tk = taken + b * words_ld; st.S = k4p_smem + (size_t)warp * nblk; st.A = A;
+    st.words = (A + 31) >> 5;
     st.blk = blk; st.per = blk / 32; st.nblk = nblk; st.c = nblk / 32; st.lane = lane;
+    st.vec_ok = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
     st.rebuild();
     uint4 rnd = make_uint4(0, 0, 0, 0);
     bool finished = false;
@@ -162,25 +194,29 @@ k4p_steps_kernel(const float* __restrict__ logits, int64_t A, uint32_t* __restri
       }
       const int o = bal ? __ffs(bal) - 1 : 31 - __clz(nzL);
       const float t3 = t2 - __shfl_sync(0xffffffffu, incL - ls, o);
-      long long pick = -1;
-      float pick_e = 0.f;
-      if (lane == o) {
-        long long lastv = -1;
-        float last_e = 0.f, acc = 0.f;
-        const int64_t lo = base + (int64_t)lane * st.per;
-        for (int i = 0; i < st.per && pick < 0; ++i) {
-          const int64_t id = lo + i;
-          if (id < A && st.untaken(id)) {
-            const float e = __expf(st.lg[id] - st.mx);
-            if (e > 0.f) { lastv = id; last_e = e; }
-            acc += e;
-            if (acc > t3 && e > 0.f) { pick = id; pick_e = e; }
-          }
+      // the whole warp walks the owner lane's ids, 32 per round
+      long long pick = -1, lastv = -1;
+      float pick_e = 0.f, last_e = 0.f, acc = 0.f;
+      const int64_t lo_o = base + (int64_t)o * st.per;
+      for (int r0 = 0; r0 < st.per && pick < 0; r0 += 32) {
+        const int64_t id = lo_o + r0 + lane;
+        const bool ok = r0 + lane < st.per && id < A && !((st.tk[id >> 5] >> (id & 31)) & 1u);
+        const float e = ok ? __expf(st.lg[id] - st.mx) : 0.f;
+        const float inc = k4p_scan(e, lane);
+        const unsigned cb = __ballot_sync(0xffffffffu, acc + inc > t3 && e > 0.f);
+        const unsigned vb = __ballot_sync(0xffffffffu, e > 0.f);
+        if (cb) {
+          const int src = __ffs(cb) - 1;
+          pick = lo_o + r0 + src;
+          pick_e = __shfl_sync(0xffffffffu, e, src);
+        } else if (vb) {
+          const int src = 31 - __clz(vb);
+          lastv = lo_o + r0 + src;
+          last_e = __shfl_sync(0xffffffffu, e, src);
         }
-        if (pick < 0) { pick = lastv; pick_e = last_e; }
+        acc += __shfl_sync(0xffffffffu, inc, 31);
       }
-      pick = __shfl_sync(0xffffffffu, pick, o);
-      pick_e = __shfl_sync(0xffffffffu, pick_e, o);
+      if (pick < 0) { pick = lastv; pick_e = last_e; }
       if (lane == 0) {
         act[s] = (OutT)pick;
         if (pr) pr[s] = pick_e / total;

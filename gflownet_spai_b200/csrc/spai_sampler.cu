@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "k4g_gumbel.cuh"
+#include "k4p_steps.cuh"
 #include "spai_internal.cuh"
 
 using namespace spai;
@@ -127,6 +128,38 @@ int spai_sample_order_dev(int device, const float* logits, int64_t A, int64_t B,
               "from spai_sample_taken_dev with the same logits / seed / sample0)", herr[1]);
     return SPAI_ERR_INVALID;
   }
+  return SPAI_OK;
+}
+
+int spai_sample_steps_dev(int device, const float* logits, int64_t A, int64_t B, uint32_t* taken, int64_t words_ld,
+                          uint8_t* done, const float* uniforms, uint64_t seed, int64_t sample0, int64_t step0,
+                          int64_t nsteps, void* actions, int id_bytes, float* probs, int64_t ld, int32_t* steps_taken,
+                          void* stream) {
+  if (!logits || !taken || !done || !actions || A <= 0 || A >= ((int64_t)1 << 31) || B < 0 || nsteps < 0 || sample0 < 0 ||
+      step0 < 0 || words_ld < (A + 31) / 32 || ld < step0 + nsteps || (id_bytes != 4 && id_bytes != 8)) {
+    set_error("spai_sample_steps_dev: invalid arguments");
+    return SPAI_ERR_INVALID;
+  }
+  if (B == 0 || nsteps == 0) return SPAI_OK;
+  Guard g(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // ~sqrt(A) ids per block (a multiple of 128: 16-byte loads per lane), at most K4P_MAX_NBLK blocks (a multiple of 32, zero-padded)
+  int64_t blk = 128;
+  while (blk * blk < A) blk += 128;
+  blk = std::max<int64_t>(blk, round_up(ceil_div(A, (int64_t)K4P_MAX_NBLK), 128));
+  const int nblk = (int)round_up(ceil_div(A, blk), 32);
+  const int smem = K4P_WARPS * nblk * (int)sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(B, (int64_t)K4P_WARPS);
+  if (id_bytes == 4)
+    k4p_steps_kernel<int32_t><<<grid, K4P_WARPS * 32, smem, st>>>(logits, A, taken, words_ld, done, uniforms, seed, sample0,
+                                                                 step0, B, nsteps, (int)blk, nblk,
+                                                                 reinterpret_cast<int32_t*>(actions), probs, ld, steps_taken);
+  else
+    k4p_steps_kernel<long long><<<grid, K4P_WARPS * 32, smem, st>>>(logits, A, taken, words_ld, done, uniforms, seed, sample0,
+                                                                   step0, B, nsteps, (int)blk, nblk,
+                                                                   reinterpret_cast<long long*>(actions), probs, ld,
+                                                                   steps_taken);
+  SPAI_CUDA(cudaGetLastError());
   return SPAI_OK;
 }
 

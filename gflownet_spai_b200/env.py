@@ -286,6 +286,27 @@ class SpaiContext:
                                               self._stream()), "spai_sample_order_dev")
         return out
 
+    def sample_steps(self, logits: torch.Tensor, taken: torch.Tensor, done: torch.Tensor, nsteps: int,
+                     uniforms: torch.Tensor | None = None, seed: int = 0, sample0: int = 0, step0: int = 0,
+                     actions: torch.Tensor | None = None, probs: torch.Tensor | None = None,
+                     dtype: torch.dtype = torch.int32, want_probs: bool = True):
+        """Up to `nsteps` masked-categorical steps per sample in one launch (K4p, spai_sample_steps_dev).
+        taken int32[B, words] / done uint8[B] are updated in place; returns (actions [B, ld], probs f32[B, ld] or
+        None, steps_taken int32[B]); columns step0 .. step0 + nsteps - 1 are written."""
+        bsz = taken.shape[0]
+        dev = logits.device
+        if actions is None:
+            actions = torch.empty((bsz, step0 + nsteps), dtype=dtype, device=dev)
+        if probs is None and want_probs:
+            probs = torch.empty((bsz, actions.shape[1]), dtype=torch.float32, device=dev)
+        steps = torch.empty(bsz, dtype=torch.int32, device=dev)
+        check(self._lib.spai_sample_steps_dev(self.device, _ptr(logits), logits.numel(), bsz, _ptr(taken), taken.shape[1],
+                                              _ptr(done), _ptr(uniforms) if uniforms is not None else None,
+                                              int(seed) & (2 ** 64 - 1), int(sample0), int(step0), int(nsteps), _ptr(actions),
+                                              actions.element_size(), _ptr(probs) if probs is not None else None,
+                                              actions.shape[1], _ptr(steps), self._stream()), "spai_sample_steps_dev")
+        return actions, probs, steps
+
     def sample_step(self, logits, taken, uniforms, done, action, prob):
         """In-place masked categorical step on CUDA tensors (include/spai_b200.h)."""
         a = logits.shape[-1]

@@ -245,6 +245,22 @@ int spai_sample_order_dev(int device, const float* logits_dev, int64_t A, int64_
                           int64_t sample0, const int32_t* length_dev, void* actions_dev, int id_bytes,
                           int64_t ld, void* stream);
 
+/* Many masked-categorical environment steps per launch (k4p_steps.cuh): the step of
+ * spai_sample_step_dev (policy.py:64-73, gflownet.py:148,:177-179, log.py:67-87) repeated up to
+ * `nsteps` times per sample with per-block running sums of exp(logit - max) kept on chip, so a step
+ * costs O(sqrt(A)) instead of three passes over the A logits. One logits vector f32[A] for all samples
+ * (the policy is constant inside sample_states). taken_dev u32[B, words_ld] and done_dev u8[B] are
+ * in/out exactly as in spai_sample_step_dev. uniforms_dev f32[nsteps, B] in [0,1) drives step s of
+ * sample b with uniforms[s * B + b]; NULL = Philox4x32-10(seed; counter = ((step0 + s) / 4, sample0 + b)).
+ * Outputs, row b, column step0 + s: actions_dev (id_bytes 4: i32, 8: i64) [B, ld] = drawn id, -1 once
+ * the sample has finished; probs_dev f32[B, ld] (may be NULL) = its masked-softmax probability, 1.0 once
+ * finished; steps_taken_dev i32[B] (may be NULL) = ids drawn in this call. A sample still not done
+ * after the call has simply used all nsteps (call again with step0 += nsteps). */
+int spai_sample_steps_dev(int device, const float* logits_dev, int64_t A, int64_t B, uint32_t* taken_dev,
+                          int64_t words_ld, uint8_t* done_dev, const float* uniforms_dev, uint64_t seed,
+                          int64_t sample0, int64_t step0, int64_t nsteps, void* actions_dev, int id_bytes,
+                          float* probs_dev, int64_t ld, int32_t* steps_taken_dev, void* stream);
+
 /* ---- Device-side ingest: the step immediately before the reward path. ----
  * All array arguments are DEVICE pointers on `device`; outputs are caller-allocated; totals that
  * size a later allocation come back through a HOST pointer (the call synchronises `stream`).

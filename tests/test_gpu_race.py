@@ -155,3 +155,99 @@ def test_order_rejects_short_ld_and_foreign_lengths(ctx):
         ctx.sample_order(lg, length, 1, 0, ld=max(1, int(length.max()) - 1))
     with pytest.raises(ValueError):
         ctx.sample_order(lg, length, 2, 0)          # lengths of another seed
+
+
+# ---------------------------------------------------------------------------------------------
+# K4p: many masked-categorical steps per launch (spai_sample_steps_dev)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a,scale", [(5, 1.0), (461, 2.0), (1500, 6.0)])
+def test_multi_step_kernel_follows_the_inverse_cdf_oracle_step_by_step(ctx, a, scale):
+    """Whole trajectories with injected uniforms: every step's id must lie in the oracle's inverse-CDF
+    interval for the ids taken so far (policy.py:64-73 masked softmax), its probability must match,
+    the terminal ends the row, -1 / 1.0 afterwards (log.py:67-87) — the K4 test, for every step."""
+    rng = np.random.default_rng(a)
+    logits = (rng.normal(size=a) * scale).astype(np.float32)
+    logits[-1] -= 2.0                                            # long trajectories
+    bsz, nsteps = 6, a + 2
+    u = rng.random((nsteps, bsz)).astype(np.float32)
+    lg = torch.from_numpy(logits).cuda()
+    words = (a + 31) // 32
+    taken = torch.zeros((bsz, words), dtype=torch.int32, device="cuda")
+    done = torch.zeros(bsz, dtype=torch.uint8, device="cuda")
+    acts, probs, steps = ctx.sample_steps(lg, taken, done, nsteps, uniforms=torch.from_numpy(u).cuda(), dtype=torch.int64)
+    acts, probs, steps = acts.cpu().numpy(), probs.cpu().numpy(), steps.cpu().numpy()
+    assert bool(done.all())
+    bits = _unpack(taken, a)
+    for b in range(bsz):
+        seen = []
+        n = int(steps[b])
+        assert acts[b, n - 1] == a - 1 and np.all(acts[b, n:] == -1) and np.all(probs[b, n:] == 1.0)
+        for s in range(n):
+            p = orc.masked_softmax_probs(logits, seen).astype(np.float64)
+            cdf = np.cumsum(p)
+            x = int(acts[b, s])
+            assert 0 <= x < a and x not in seen
+            lo = cdf[x - 1] if x else 0.0
+            tgt = float(u[s, b]) * cdf[-1]
+            assert lo - 2e-5 <= tgt <= cdf[x] + 2e-5
+            assert probs[b, s] == pytest.approx(p[x] / cdf[-1], rel=5e-4, abs=1e-7)
+            seen.append(x)
+        want = np.zeros(a, dtype=bool)
+        want[seen] = True
+        assert np.array_equal(bits[b], want)
+
+
+def test_multi_step_kernel_resumes_and_matches_single_launch(ctx):
+    """nsteps split over several launches (step0 advancing) draws the same trajectory as one launch
+    (Philox uniforms are a function of (seed, sample, step)); finished samples are left alone."""
+    a = 3001
+    lg = torch.randn(a, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+    bsz, total = 9, a + 1
+    words = (a + 31) // 32
+    t1 = torch.zeros((bsz, words), dtype=torch.int32, device="cuda")
+    d1 = torch.zeros(bsz, dtype=torch.uint8, device="cuda")
+    a1, p1, s1 = ctx.sample_steps(lg, t1, d1, total, seed=42, sample0=100)
+    t2 = torch.zeros_like(t1)
+    d2 = torch.zeros_like(d1)
+    a2 = torch.empty((bsz, total), dtype=torch.int32, device="cuda")
+    p2 = torch.empty((bsz, total), dtype=torch.float32, device="cuda")
+    step0 = 0
+    for chunk in (1, 7, 500, total - 508):
+        ctx.sample_steps(lg, t2, d2, chunk, seed=42, sample0=100, step0=step0, actions=a2, probs=p2)
+        step0 += chunk
+    assert bool(d1.all()) and bool(d2.all())
+    assert torch.equal(a1, a2) and torch.equal(t1, t2)
+    assert torch.allclose(p1, p2, rtol=1e-5, atol=1e-9)
+    # every row: distinct ids, terminal last
+    for b in range(bsz):
+        n = int(s1[b])
+        row = a1[b, :n].tolist()
+        assert len(set(row)) == n and row[-1] == a - 1
+
+
+def test_multi_step_kernel_at_cfg2_size_probabilities(ctx):
+    """A = 524 281 (cfg2): 3000 steps of 8 samples; ids distinct, and the reported probability equals
+    p[a_t] / (mass not yet taken) computed in float64 on the device."""
+    a = 524281
+    lg = torch.randn(a, generator=torch.Generator(device="cuda").manual_seed(2), device="cuda") * 0.5
+    lg[-1] = -30.0                                               # the terminal practically never comes up
+    bsz, nsteps = 8, 3000
+    words = (a + 31) // 32
+    taken = torch.zeros((bsz, words), dtype=torch.int32, device="cuda")
+    done = torch.zeros(bsz, dtype=torch.uint8, device="cuda")
+    acts, probs, steps = ctx.sample_steps(lg, taken, done, nsteps, seed=5)
+    assert int(steps.min()) == nsteps and not bool(done.any())
+    p = torch.softmax(lg.double(), 0)
+    pa = p[acts.long()]
+    rest = 1.0 - (torch.cumsum(pa, 1) - pa)
+    assert torch.allclose(probs.double(), pa / rest, rtol=2e-4)
+    srt = torch.sort(acts, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # first ids ~ softmax: the mean log-probability of the first draw is close to its expectation
+    many_t = torch.zeros((4096, words), dtype=torch.int32, device="cuda")
+    many_d = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    a1, _, _ = ctx.sample_steps(lg, many_t, many_d, 1, seed=6, want_probs=False)
+    got = float(torch.log(p[a1[:, 0].long()]).mean())
+    want = float((p * torch.log(p)).sum())
+    sd = float(((p * torch.log(p) ** 2).sum() - want ** 2).sqrt()) / 64.0
+    assert abs(got - want) < 5 * sd
