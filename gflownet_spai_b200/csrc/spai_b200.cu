@@ -17,6 +17,7 @@
 #include "k3_copy.cuh"
 #include "k3s_sparse.cuh"
 #include "k3t_lut.cuh"
+#include "k3m_mma.cuh"
 #include "k4_sample.cuh"
 #include "spai_internal.cuh"
 
@@ -595,6 +596,10 @@ struct PhaseTimer {
 
 // Reward of Bc trajectories whose slot-order masks mask[Bc][W] are already built.
 // `scratch` has at least eval_bytes(); outputs are device pointers (may be null).
+static inline bool k3m_on() {
+  const char* e = getenv("SPAI_K3_MMA");
+  return !e || atoi(e) != 0;
+}
 static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, const uint32_t* mask,
                       int64_t Bc, char* scratch, int64_t scratch_bytes, int sm_count, double n_d,
                       double res0, double flops0, double alpha, double* reward, double* residual,
@@ -698,6 +703,48 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
       if (s.nt == 4) SPAI_K3T(double, 4); else if (s.nt == 2) SPAI_K3T(double, 2); else SPAI_K3T(double, 1);
     }
 #undef SPAI_K3T
+    SPAI_CUDA(cudaGetLastError()); ++nl;
+    parts = gx;
+  } else if (mode == SPAI_MODE_COPY && dtype == SPAI_F32 && plan.mma_ready && plan.tables_on && k3m_on() && Bc >= 64) {
+    // tensor-core row residuals (K3m): one wave of CTAs over (row ranges) x (128 * NTM trajectories)
+    const int64_t rows = row_hi - row_lo;
+    const int ntm_max = std::min(s.nt, plan.mma_n == 16 ? 4 : 2);
+    int ntm = std::min(ntm_max, 2);
+    if (const char* v = getenv("SPAI_K3M_NTM")) ntm = std::max(1, std::min(ntm_max, atoi(v)));      // A/B switch
+    const int gy = (int)(Bp / ((int64_t)128 * ntm));
+    int gx = 1;
+    const void* fn = nullptr;
+    size_t smem = 0;
+#define SPAI_K3M_PICK(N_, S_, NTM_)                                                      \
+  do { fn = (const void*)k3m_kernel<N_, S_, NTM_>; smem = (size_t)k3m_smem_bytes<N_, S_, NTM_>(); } while (0)
+#define SPAI_K3M_CLASS(N_)                                                               \
+  do {                                                                                   \
+    if (plan.mma_split == 2) { if (ntm >= 4) SPAI_K3M_PICK(N_, 2, 4); else if (ntm == 2) SPAI_K3M_PICK(N_, 2, 2); else SPAI_K3M_PICK(N_, 2, 1); } \
+    else { if (ntm >= 4) SPAI_K3M_PICK(N_, 3, 4); else if (ntm == 2) SPAI_K3M_PICK(N_, 3, 2); else SPAI_K3M_PICK(N_, 3, 1); }                       \
+  } while (0)
+    if (ntm == 3) ntm = 2;
+    if (plan.mma_n == 16) SPAI_K3M_CLASS(16); else SPAI_K3M_CLASS(32);
+#undef SPAI_K3M_CLASS
+#undef SPAI_K3M_PICK
+    SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, K3M_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    per_sm = std::min(per_sm, 512 / std::max(32, (plan.mma_n == 16 ? 4 : 2) * ntm * plan.mma_n));   // TMEM columns per SM
+    if (rows > 0)
+      gx = (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)s.parts}));
+    if (rows <= 0) {
+      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st));
+    } else {
+      const unsigned char* recp = plan.mma_rec;
+      int rlo = (int)row_lo, rhi = (int)row_hi;
+      int64_t bp_ = Bp, w_ = W;
+      const uint32_t* mt = maskT;
+      double* pp = partial;
+      const RowHdr* rh = plan.rhdr;
+      void* args[] = {(void*)&recp, (void*)&rh, (void*)&mt, (void*)&bp_, (void*)&w_, (void*)&pp, (void*)&rlo, (void*)&rhi};
+      SPAI_CUDA(cudaLaunchKernel(fn, dim3(gx, gy), dim3(K3M_THREADS), args, smem, st));
+    }
     SPAI_CUDA(cudaGetLastError()); ++nl;
     parts = gx;
   } else if (mode == SPAI_MODE_COPY) {
@@ -1005,6 +1052,46 @@ static int ensure_lut(spai_ctx* c, int dtype, cudaStream_t st) {
   SPAI_CUDA(cudaGetLastError());
   plan.bytes = ar.bytes;
   plan.lut_ready = true;
+  return SPAI_OK;
+}
+
+// K3m records: per-row Cholesky factor of the Gram matrix of the row's candidate contributions, bf16-split,
+// in the UMMA canonical layout (k3m_mma.cuh). fp32 copy mode only.
+static bool k3m_enabled() {                  // A/B + test switch: SPAI_K3_MMA=0 keeps the row sweep (K3)
+  const char* e = getenv("SPAI_K3_MMA");
+  return !e || atoi(e) != 0;
+}
+static int k3m_split() {
+  const char* e = getenv("SPAI_K3M_SPLIT");
+  const int v = e ? atoi(e) : 3;
+  return v == 2 ? 2 : 3;
+}
+static int ensure_mma(spai_ctx* c, int dtype, cudaStream_t st) {
+  Plan& plan = c->plan[dtype];
+  if (plan.mma_ready || plan.mma_unavailable || dtype != SPAI_F32) return SPAI_OK;
+  const int64_t n = c->P.n;
+  const int split = k3m_split();
+  if (n == 0 || c->P.ndup || c->P.max_k > 32 || !plan.c_col || !plan.rec_copy) { plan.mma_unavailable = true; return SPAI_OK; }
+  const int N = c->P.max_k <= 16 ? 16 : 32;
+  const int64_t rb = N == 16 ? (split == 2 ? K3mGeom<16, 2>::RB : K3mGeom<16, 3>::RB)
+                             : (split == 2 ? K3mGeom<32, 2>::RB : K3mGeom<32, 3>::RB);
+  if (n * rb > ((int64_t)24 << 30)) { plan.mma_unavailable = true; return SPAI_OK; }
+  Arena& ar = c->plan_arena[dtype];
+  unsigned char* rec = nullptr;
+  SPAI_TRY(ar.alloc(&rec, n * rb));
+  const Rec32* rc = reinterpret_cast<const Rec32*>(plan.rec_copy);
+  const unsigned blocks = (unsigned)ceil_div(n, 4);
+  if (N == 16 && split == 2) k3m_build_kernel<16, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
+  else if (N == 16) k3m_build_kernel<16, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
+  else if (split == 2) k3m_build_kernel<32, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
+  else k3m_build_kernel<32, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
+  SPAI_CUDA(cudaGetLastError());
+  SPAI_CUDA(cudaStreamSynchronize(st));            // one-time build: later calls on other streams see a finished table
+  plan.mma_rec = rec;
+  plan.mma_n = N;
+  plan.mma_split = split;
+  plan.bytes = ar.bytes;
+  plan.mma_ready = true;
   return SPAI_OK;
 }
 
@@ -1537,6 +1624,8 @@ static int reward_driver(spai_ctx* c, const RewardCall& rc) {
   if (!mask_only && mode == SPAI_MODE_LS_GRAM && B >= 64) SPAI_TRY(ensure_lut_ls(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_LS && B >= 64) SPAI_TRY(ensure_lut_qr(c, dtype, st));
   if (!mask_only && mode == SPAI_MODE_COPY && B >= 64) SPAI_TRY(ensure_lut(c, dtype, st));
+  if (!mask_only && mode == SPAI_MODE_COPY && dtype == SPAI_F32 && B >= 64 && !c->plan[dtype].lut_ready && k3m_enabled())
+    SPAI_TRY(ensure_mma(c, dtype, st));
   if (!mask_only) c->plan[dtype].tables_on = B >= 64;
   int64_t t_len = rc.t_hint;                                   // longest trajectory (0 = unknown)
   if (src != FROM_TAKEN_DEV) {

@@ -154,6 +154,11 @@ struct Plan {
   void* lut_ls = nullptr;
   bool lut_qr_ready = false;                         // ls mode: filled by the Householder kernel, always f64[n][256]
   double* lut_qr = nullptr;
+  // tensor-core copy kernel (K3m, fp32, rows with <= 32 candidates, no repeated coordinates; built on first use)
+  bool mma_ready = false;
+  bool mma_unavailable = false;
+  unsigned char* mma_rec = nullptr;                  // [n][K3mGeom::RB]
+  int mma_n = 0, mma_split = 0;                      // N = 16 (KP = 32) or 32 (KP = 48); bf16 terms per entry of L
   // deletion-driven copy kernel (K3s, built on first use)
   bool sparse_ready = false;
   bool sparse_unavailable = false;                   // a row of A or of the pattern exceeds the SlotMeta fields
