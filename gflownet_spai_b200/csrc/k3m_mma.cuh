@@ -8,14 +8,15 @@
 // With the Cholesky factor G = L L^T and L v = g (both once per context, fp64, semi-definite safe)
 //     r_i(kappa) = || L^T kappa - v ||^2 + c,   c = [i in union] - |v|^2 >= 0 (the row's least-squares optimum)
 // — a sum of squares, no cancellation. For 128 trajectories at once, Z = kappa * L is ONE small dense
-// contraction with an exact 0/1 operand: A = kappa as bf16 (built in shared memory from the kept-mask bits),
-// B = L split into NSPLIT bf16 terms (every product exact, fp32 accumulation in TMEM), M = 128 trajectories,
-// N = K = 16 or 32. The epilogue reads its trajectory's N accumulators (tcgen05.ld 32x32b), subtracts v and
-// adds N squares.
+// contraction with an exact operand: A = 2*kappa as bf16 (0x4000 per kept bit, written straight into TENSOR
+// MEMORY by the thread that owns the trajectory's lane: tcgen05.st, no shared-memory traffic for A),
+// B = L/2 split into NSPLIT bf16 terms (every product exact, fp32 accumulation in TMEM), M = 128 trajectories,
+// N = K = 16 or 32 (tcgen05.mma with the A operand in TMEM). The epilogue reads its trajectory's N
+// accumulators (tcgen05.ld 32x32b), subtracts v and adds N squares.
 //
 // Warp-specialised CTA (288 threads), rows flow through three mbarrier rings without a block barrier:
 //   warps 4-7  producers: kept-mask words (cp.async into a private shared-memory window, two chunks of 8
-//              words in flight) -> the row's k bits -> bf16 A tiles (byte -> 16-byte LUT) -> fence.proxy.async
+//              words in flight) -> the row's k bits -> bf16 pairs (one 64-bit multiply per 4 bits) -> tcgen05.st
 //   warp 8     one thread: cp.async.bulk of the record stages, tcgen05.mma issue, tcgen05.commit
 //   warps 0-3  epilogue: tcgen05.ld of their TMEM lane quarter, (z - v)^2 sums, fixed-order partial sums
 // fp32 only (fp64 stays on K3); rows with repeated coordinates keep K3.
@@ -38,12 +39,10 @@ struct K3mGeom {
   static constexpr int TILE_B = N * KP * 2;                    // one bf16 term of L, canonical K-major core-matrix layout
   static constexpr int TAIL = 16 + 4 * N;                      // {c, pad[3], v[N]}
   static constexpr int RB = NSPLIT * TILE_B + TAIL;
-  static constexpr int RPS = N == 16 ? 8 : 2;                  // rows per bulk-copied stage (~13 KB)
+  static constexpr int RPS = N == 16 ? 4 : 1;                  // rows per bulk-copied stage (~6.4 KB)
   static constexpr int STAGE = (RPS * RB + 127) / 128 * 128;
-  static constexpr int TILE_A = 128 * KP * 2;
-  static constexpr int SBO = (KP / 8) * 128;                   // stride between 8-row groups (both operands)
-  static constexpr int NA = N == 16 ? 4 : 3;                   // A-tile ring depth (rows)
-  static constexpr int NACC = N == 16 ? 4 : 2;                 // accumulator ring depth (rows)
+  static constexpr int SBO = (KP / 8) * 128;                   // stride between 8-row groups of B
+  static constexpr int ACOLS = KP / 2;                         // TMEM columns of one A tile (two bf16 per column)
   static_assert(N == 16 || N == 32, "N");
 };
 struct K3mTail { float c; int32_t sp; int32_t k; int32_t pad; };   // followed by float v[N]
@@ -56,7 +55,20 @@ __host__ __device__ constexpr int k3m_off(int row, int kk, int KP) {
 template <int N, int NSPLIT, int NTM>
 __host__ __device__ constexpr int k3m_smem_bytes() {
   using G = K3mGeom<N, NSPLIT>;
-  return 256 + 4096 + K3M_NSTAGE * G::STAGE + G::NA * NTM * G::TILE_A + 2 * (K3M_MW + 1) * 128 * NTM * 4;
+  return 512 + K3M_NSTAGE * G::STAGE + 2 * (K3M_MW + 1) * 128 * NTM * 4;
+}
+// ring depth (rows in flight) of the A tiles and of the accumulators: as deep as 512 TMEM columns allow, at most 8
+// ring depth (rows in flight) of the A tiles and of the accumulators
+template <int N, int NTM>
+__host__ __device__ constexpr int k3m_depth() {
+  return 2;                                                   // measured: depths 4 and 8 are no faster; 2 keeps the TMEM
+                                                              // allocation small enough for 2-4 CTAs per SM
+}
+template <int N, int NTM>
+__host__ __device__ constexpr int k3m_tmem_cols() {           // accumulator ring + A ring, rounded to an allocation size
+  const int raw = k3m_depth<N, NTM>() * NTM * (N + N / 2);
+  static_assert(k3m_depth<N, NTM>() * NTM * (N + N / 2) <= 512, "TMEM");
+  return raw <= 32 ? 32 : raw <= 64 ? 64 : raw <= 128 ? 128 : raw <= 256 ? 256 : 512;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -117,7 +129,7 @@ k3m_build_kernel(const Rec32* __restrict__ recs, const int64_t* __restrict__ cpt
   for (int idx = lane; idx < N * KP; idx += 32) {
     const int nn = idx / KP, kk = idx % KP;                    // B[nn][kk] = L[kk][nn]
     double x = 0.0;
-    if (kk < k && nn <= kk) x = G[kk * LD + nn];
+    if (kk < k && nn <= kk) x = 0.5 * G[kk * LD + nn];          // the A operand carries 2 * kappa
     const int off = k3m_off(nn, kk, KP);
 #pragma unroll
     for (int s = 0; s < NSPLIT; ++s) {
@@ -150,13 +162,33 @@ __device__ __forceinline__ uint64_t k3m_desc(uint32_t smem_addr, uint32_t lbo, u
 __host__ __device__ constexpr uint32_t k3m_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void k3m_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor given as its two 32-bit halves]; ACC = 0 overwrites D
+template <int ACC>
+__device__ __forceinline__ void k3m_mma(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, {%6, %6, %6, %6}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC), "r"(0u)
       : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void k3m_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 kept bits -> 16 bf16 (0x4000 = 2.0 per set bit), two elements per word: one 64-bit multiply spreads 4 bits
+__device__ __forceinline__ void k3m_expand16(uint32_t bits, uint32_t (&w)[8]) {
+  constexpr unsigned long long M = (1ull << 14) | (1ull << 29) | (1ull << 44) | (1ull << 59);
+  constexpr unsigned long long MASK = 0x4000400040004000ull;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const unsigned long long p = ((unsigned long long)((bits >> (4 * q)) & 0xfu) * M) & MASK;
+    w[2 * q] = (uint32_t)p;
+    w[2 * q + 1] = (uint32_t)(p >> 32);
+  }
 }
 __device__ __forceinline__ void k3m_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -183,25 +215,24 @@ __device__ __forceinline__ void k3m_cp4(void* dst, const void* src) {
 }
 
 template <int N, int NSPLIT, int NTM>
-__global__ void __launch_bounds__(K3M_THREADS)
+__global__ void __launch_bounds__(K3M_THREADS, 2)
 k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rhdr, const uint32_t* __restrict__ maskT,
-           int64_t Bp, int64_t W, double* __restrict__ partial, int row_lo, int row_hi) {
+           int64_t Bp, int64_t W, double* __restrict__ partial, int row_lo, int row_hi, int dbg) {
   using Geo = K3mGeom<N, NSPLIT>;
-  constexpr int KP = Geo::KP, RPS = Geo::RPS, NA = Geo::NA, NACC = Geo::NACC;
-  constexpr int TCOLS_RAW = NACC * NTM * N;
-  constexpr uint32_t TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  constexpr int KP = Geo::KP, RPS = Geo::RPS, NA = k3m_depth<N, NTM>(), NACC = NA;
+  constexpr int NW = N;                                                // accumulator columns of one (row, tile)
+  constexpr uint32_t TCOLS = (uint32_t)k3m_tmem_cols<N, NTM>();
+  constexpr uint32_t ACOL0 = NACC * NTM * NW;                            // the A ring follows the accumulator ring
   extern __shared__ __align__(128) unsigned char k3m_smem[];
   uint64_t* bfull = reinterpret_cast<uint64_t*>(k3m_smem);             // [NSTAGE] record stage landed (tx)
   uint64_t* bempty = bfull + K3M_NSTAGE;                               // [NSTAGE] 128 epilogue threads are done with it
-  uint64_t* afull = bempty + K3M_NSTAGE;                               // [NA] 128 producer threads wrote the row's A tiles
-  uint64_t* aempty = afull + 4;                                        // [NA] the MMAs that read them have completed
-  uint64_t* accfull = aempty + 4;                                      // [NACC] the row's accumulators are complete
-  uint64_t* accempty = accfull + 4;                                    // [NACC] 128 epilogue threads have read them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 4);
-  uint4* lut = reinterpret_cast<uint4*>(k3m_smem + 256);               // byte -> 8 bf16 (0.0 / 1.0)
-  unsigned char* ring = k3m_smem + 256 + 4096;
-  unsigned char* abuf = ring + K3M_NSTAGE * Geo::STAGE;
-  uint32_t* mwin = reinterpret_cast<uint32_t*>(abuf + NA * NTM * Geo::TILE_A);   // [2][MW + 1][128 * NTM]
+  uint64_t* afull = bempty + K3M_NSTAGE;                               // [NA] 128 producer threads stored the row's A tiles (TMEM)
+  uint64_t* aempty = afull + 8;                                        // [NA] the MMAs that read them have completed
+  uint64_t* accfull = aempty + 8;                                      // [NACC] the row's accumulators are complete
+  uint64_t* accempty = accfull + 8;                                    // [NACC] 128 epilogue threads have read them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 8);
+  unsigned char* ring = k3m_smem + 512;
+  uint32_t* mwin = reinterpret_cast<uint32_t*>(ring + K3M_NSTAGE * Geo::STAGE);   // [2][MW + 1][128 * NTM]
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t nrows_all = row_hi - row_lo;
@@ -212,16 +243,10 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
   const int64_t bbase = (int64_t)blockIdx.y * (128 * NTM);
 
   if (tid == 0) {
-    for (int i = 0; i < K3M_NSTAGE; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 128); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 128); mbar_init(&aempty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 128); }
+    for (int i = 0; i < K3M_NSTAGE; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 4); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 4); }
     mbar_fence_init();
-  }
-  for (int e = tid; e < 256; e += K3M_THREADS) {
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = (((e >> (2 * q)) & 1) ? 0x3f80u : 0u) | (((e >> (2 * q + 1)) & 1) ? 0x3f800000u : 0u);
-    lut[e] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS));
@@ -256,22 +281,24 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
         mbar_wait(&afull[it % NA], (uint32_t)((it / NA) & 1));
         mbar_wait(&accempty[it % NACC], (uint32_t)(((it / NACC) & 1) ^ 1));
         k3m_fence_after();
-        const uint32_t brow = smem_u32(ring + (size_t)(m % K3M_NSTAGE) * Geo::STAGE + (size_t)(it % RPS) * Geo::RB);
-        const uint32_t abase = smem_u32(abuf + (size_t)(it % NA) * NTM * Geo::TILE_A);
+        // descriptor of the row's first B tile; the other tiles differ in the 14-bit start-address field only
+        const uint32_t blo = ((smem_u32(ring) + (uint32_t)((m % K3M_NSTAGE) * Geo::STAGE + (it % RPS) * Geo::RB)) >> 4) | ((128u >> 4) << 16);
+        constexpr uint32_t BHI = ((uint32_t)Geo::SBO >> 4) | (1u << 14);      // stride byte offset, descriptor version 1
+        const uint32_t abase = tmem + ACOL0 + (uint32_t)((it % NA) * NTM * Geo::ACOLS);
+        const uint32_t dbase = tmem + (uint32_t)((it % NACC) * NTM * NW);
+        // the NSPLIT terms accumulate into the same N columns; consecutive MMAs go to DIFFERENT tiles, so an MMA never
+        // waits for the one issued just before it (back-to-back accumulation into one tile cost ~45 cycles per MMA)
+        if (!(dbg & 1))
 #pragma unroll
-        for (int j = 0; j < NTM; ++j) {
-          const uint32_t dcol = tmem + (uint32_t)((it % NACC) * NTM * N + j * N);
-          uint32_t acc = 0;
+        for (int s = 0; s < NSPLIT; ++s)
 #pragma unroll
-          for (int s = 0; s < NSPLIT; ++s)
+          for (int ks = 0; ks < KP / 16; ++ks)
 #pragma unroll
-            for (int ks = 0; ks < KP / 16; ++ks) {
-              k3m_mma(dcol, k3m_desc(abase + j * Geo::TILE_A + ks * 256, 128, Geo::SBO),
-                      k3m_desc(brow + s * Geo::TILE_B + ks * 256, 128, Geo::SBO), IDESC, acc);
-              acc = 1;
+            for (int j = 0; j < NTM; ++j) {
+              const uint32_t bl = blo + (uint32_t)((s * Geo::TILE_B + ks * 256) >> 4);
+              if (s == 0 && ks == 0) k3m_mma<0>(dbase + j * NW, abase + j * Geo::ACOLS + ks * 8, bl, BHI, IDESC);
+              else k3m_mma<1>(dbase + j * NW, abase + j * Geo::ACOLS + ks * 8, bl, BHI, IDESC);
             }
-        }
-        k3m_commit(&aempty[it % NA]);
         k3m_commit(&accfull[it % NACC]);
       }
     }
@@ -296,9 +323,17 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
     fetch(0, wb);
     fetch(1, wb + K3M_MW);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
+    // row headers: lane l of every producer warp holds the header of row (block * 32 + l); the next block of 32 is in
+    // flight while this one is consumed (one coalesced 512-byte load per 32 rows instead of a dependent load per row)
+    const int lane = tid & 31;
+    auto hload = [&](int blk) {
+      const int i = blk * 32 + lane;
+      return i < nrows ? __ldg(reinterpret_cast<const int4*>(rhdr + r0 + i)) : make_int4(0, 0, 0, 0);
+    };
+    int4 hcur = hload(0), hnext = hload(1);
     for (int it = 0; it < nrows; ++it) {
-      const int4 hraw = __ldg(reinterpret_cast<const int4*>(rhdr + r0 + it));
-      const int sp = hraw.y, k = hraw.z;
+      if (it && (it & 31) == 0) { hcur = hnext; hnext = hload((it >> 5) + 1); }
+      const int sp = __shfl_sync(0xffffffffu, hcur.y, it & 31), k = __shfl_sync(0xffffffffu, hcur.z, it & 31);
       const int64_t wd = sp >> 5;
       while (wd - wb >= K3M_MW) {                                       // the row's two words must lie in [wb, wb + MW]
         wb += K3M_MW;
@@ -312,15 +347,24 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
       uint32_t bits[NTM];
 #pragma unroll
       for (int j = 0; j < NTM; ++j) bits[j] = __funnelshift_r(wp[j * 128], wp[128 * NTM + j * 128], sh) & kmask;
-      mbar_wait(&aempty[it % NA], (uint32_t)(((it / NA) & 1) ^ 1));
-      unsigned char* a0 = abuf + (size_t)(it % NA) * NTM * Geo::TILE_A + (t >> 3) * Geo::SBO + (t & 7) * 16;
+      // the A slot of row it - NA is free once that row's MMAs have completed: the same tcgen05.commit that publishes its
+      // accumulators (one commit per row; NA == NACC)
+      if (it >= NA) mbar_wait(&accfull[it % NA], (uint32_t)(((it / NA) - 1) & 1));
+      k3m_fence_after();
+      const uint32_t a0 = tmem + ((uint32_t)((warp - 4) * 32) << 16) + ACOL0 + (uint32_t)((it % NA) * NTM * Geo::ACOLS);
+      if (!(dbg & 2))
 #pragma unroll
       for (int j = 0; j < NTM; ++j)
 #pragma unroll
-        for (int c = 0; c < KP / 8; ++c)
-          *reinterpret_cast<uint4*>(a0 + (size_t)j * Geo::TILE_A + c * 128) = lut[(bits[j] >> (8 * c)) & 0xffu];
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
-      k3m_arrive(&afull[it % NA]);
+        for (int h = 0; h < KP / 16; ++h) {
+          uint32_t w[8];
+          k3m_expand16(bits[j] >> (16 * h), w);
+          k3m_st8(a0 + (uint32_t)(j * Geo::ACOLS + h * 8), w);
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      k3m_fence_before();
+      __syncwarp();
+      if (lane == 0) k3m_arrive(&afull[it % NA]);                    // one arrival per producer warp
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
@@ -336,13 +380,21 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
       mbar_wait(&accfull[it % NACC], (uint32_t)((it / NACC) & 1));
       k3m_fence_after();
       float z[NTM][N];
+      if (!(dbg & 4)) {
 #pragma unroll
-      for (int j = 0; j < NTM; ++j)
+        for (int j = 0; j < NTM; ++j)
 #pragma unroll
-        for (int q0 = 0; q0 < N; q0 += 16) k3m_ld16(lane_addr + (uint32_t)((it % NACC) * NTM * N + j * N + q0), &z[j][q0]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int q0 = 0; q0 < N; q0 += 16) k3m_ld16(lane_addr + (uint32_t)((it % NACC) * NTM * NW + j * NW + q0), &z[j][q0]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < NTM; ++j)
+#pragma unroll
+          for (int q = 0; q < N; ++q) z[j][q] = (float)(it + q);
+      }
       k3m_fence_before();
-      k3m_arrive(&accempty[it % NACC]);                                // the accumulators are in registers
+      __syncwarp();
+      if ((tid & 31) == 0) k3m_arrive(&accempty[it % NACC]);           // the accumulators are in registers (one arrival per warp)
       const unsigned char* tl = ring + (size_t)slot * Geo::STAGE + (size_t)(it % RPS) * Geo::RB + NSPLIT * Geo::TILE_B;
       const float c = reinterpret_cast<const K3mTail*>(tl)->c;
       const float4* vv = reinterpret_cast<const float4*>(tl + 16);
@@ -361,7 +413,10 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
           r[j] = fmaf(d3, d3, r[j]);
         }
       }
-      if (it % RPS == RPS - 1 || it == nrows - 1) k3m_arrive(&bempty[slot]);
+      if (it % RPS == RPS - 1 || it == nrows - 1) {
+        __syncwarp();
+        if ((tid & 31) == 0) k3m_arrive(&bempty[slot]);
+      }
 #pragma unroll
       for (int j = 0; j < NTM; ++j) rs[j] += r[j];
       if ((it & 15) == 15) {

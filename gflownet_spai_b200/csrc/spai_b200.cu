@@ -708,29 +708,46 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   } else if (mode == SPAI_MODE_COPY && dtype == SPAI_F32 && plan.mma_ready && plan.tables_on && k3m_on() && Bc >= 64) {
     // tensor-core row residuals (K3m): one wave of CTAs over (row ranges) x (128 * NTM trajectories)
     const int64_t rows = row_hi - row_lo;
-    const int ntm_max = std::min(s.nt, plan.mma_n == 16 ? 4 : 2);
-    int ntm = std::min(ntm_max, 2);
+    const int ntm_max = std::min(s.nt, 4);
+    int ntm = ntm_max;
     if (const char* v = getenv("SPAI_K3M_NTM")) ntm = std::max(1, std::min(ntm_max, atoi(v)));      // A/B switch
+    if (ntm == 3) ntm = 2;
+    if (plan.mma_n == 32 && ntm > 2) ntm = 2;                 // 512 TMEM columns: up to 96 + 16 per (row, tile) at N = 32
     const int gy = (int)(Bp / ((int64_t)128 * ntm));
     int gx = 1;
     const void* fn = nullptr;
     size_t smem = 0;
+    int tcols = 512;
 #define SPAI_K3M_PICK(N_, S_, NTM_)                                                      \
-  do { fn = (const void*)k3m_kernel<N_, S_, NTM_>; smem = (size_t)k3m_smem_bytes<N_, S_, NTM_>(); } while (0)
+  do { fn = (const void*)k3m_kernel<N_, S_, NTM_>; smem = (size_t)k3m_smem_bytes<N_, S_, NTM_>(); tcols = k3m_tmem_cols<N_, NTM_>(); } while (0)
 #define SPAI_K3M_CLASS(N_)                                                               \
   do {                                                                                   \
-    if (plan.mma_split == 2) { if (ntm >= 4) SPAI_K3M_PICK(N_, 2, 4); else if (ntm == 2) SPAI_K3M_PICK(N_, 2, 2); else SPAI_K3M_PICK(N_, 2, 1); } \
-    else { if (ntm >= 4) SPAI_K3M_PICK(N_, 3, 4); else if (ntm == 2) SPAI_K3M_PICK(N_, 3, 2); else SPAI_K3M_PICK(N_, 3, 1); }                       \
+    if (plan.mma_split == 2) { if (ntm == 2) SPAI_K3M_PICK(N_, 2, 2); else SPAI_K3M_PICK(N_, 2, 1); } \
+    else { if (ntm == 2) SPAI_K3M_PICK(N_, 3, 2); else SPAI_K3M_PICK(N_, 3, 1); }                       \
   } while (0)
-    if (ntm == 3) ntm = 2;
-    if (plan.mma_n == 16) SPAI_K3M_CLASS(16); else SPAI_K3M_CLASS(32);
+    if (plan.mma_n == 16 && ntm >= 4) {
+      if (plan.mma_split == 2) SPAI_K3M_PICK(16, 2, 4); else SPAI_K3M_PICK(16, 3, 4);
+    } else if (plan.mma_n == 16) SPAI_K3M_CLASS(16);
+    else SPAI_K3M_CLASS(32);
 #undef SPAI_K3M_CLASS
 #undef SPAI_K3M_PICK
     SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, K3M_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
-    per_sm = std::min(per_sm, 512 / std::max(32, (plan.mma_n == 16 ? 4 : 2) * ntm * plan.mma_n));   // TMEM columns per SM
+    const int occ_api = per_sm;
+    {                                             // resident CTAs from the kernel's own resources (the occupancy API answered 1
+      cudaFuncAttributes fa;                      // for a 288-thread, 70 KB, 70-register kernel on this driver)
+      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) {
+        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * ((K3M_THREADS + 31) / 32 * 32));
+        const int by_smem = (int)((227 * 1024) / (smem + 1024));
+        per_sm = std::max(1, std::min({by_regs, by_smem, 2048 / K3M_THREADS}));
+      } else cudaGetLastError();
+    }
+    per_sm = std::max(1, std::min(per_sm, 512 / tcols));                          // TMEM columns per SM
+    if (getenv("SPAI_K3M_VERBOSE"))
+      fprintf(stderr, "[k3m] N=%d split=%d ntm=%d smem=%zu tmem_cols=%d occupancy(api)=%d ctas/SM=%d gy=%d gx=%d\n", plan.mma_n,
+              plan.mma_split, ntm, smem, tcols, occ_api, per_sm, gy, (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)s.parts})));
     if (rows > 0)
       gx = (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)s.parts}));
     if (rows <= 0) {
@@ -742,7 +759,9 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
       const uint32_t* mt = maskT;
       double* pp = partial;
       const RowHdr* rh = plan.rhdr;
-      void* args[] = {(void*)&recp, (void*)&rh, (void*)&mt, (void*)&bp_, (void*)&w_, (void*)&pp, (void*)&rlo, (void*)&rhi};
+      int dbg = 0;
+      if (const char* v = getenv("SPAI_K3M_DEBUG")) dbg = atoi(v);                // timing experiments only (results are wrong)
+      void* args[] = {(void*)&recp, (void*)&rh, (void*)&mt, (void*)&bp_, (void*)&w_, (void*)&pp, (void*)&rlo, (void*)&rhi, (void*)&dbg};
       SPAI_CUDA(cudaLaunchKernel(fn, dim3(gx, gy), dim3(K3M_THREADS), args, smem, st));
     }
     SPAI_CUDA(cudaGetLastError()); ++nl;

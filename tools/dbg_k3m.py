@@ -11,17 +11,17 @@ pb = synth.make_problem(cfg, 1.0)
 coo = pb.a.tocoo()
 dev = torch.device("cuda", 0)
 acts, lens = bench.device_trajectories(pb.num_edges, batch, 0, dev, 0.5)
-os.environ["SPAI_K3M_SPLIT"] = "3"
+os.environ["SPAI_K3M_SPLIT"] = sys.argv[3] if len(sys.argv) > 3 else "3"
 ctx = SpaiContext(pb.n, pb.edge_row, pb.edge_col, pb.edge_val, coo.row, coo.col, coo.data, device=0)
 ctx.enable_timing(True)
-for ntm in ("4", "2", "1"):
+for ntm in ("4", "2"):
     os.environ["SPAI_K3M_NTM"] = ntm
-    for dbg in (0, 1, 2, 4, 8, 3, 7, 15):
+    for dbg in (0, 1, 2, 4, 3, 5, 6, 7):
         os.environ["SPAI_K3M_DEBUG"] = str(dbg)
         ms = []
         for it in range(3):
             ctx.reward_batch(acts, 0.5, "copy", torch.float32, lengths=lens)
             torch.cuda.synchronize()
             if it: ms.append(ctx.last_timing().ms_reward)
-        print(json.dumps({"ntm": ntm, "dbg(1=noMMA 2=noSTS 4=noLD 8=noMaskLoad)": dbg, "reward_ms": float(np.median(ms))}), flush=True)
+        print(json.dumps({"ntm": ntm, "dbg(1=noMMA 2=noSTTM 4=noLDTM)": dbg, "reward_ms": float(np.median(ms))}), flush=True)
 ctx.close()
