@@ -385,13 +385,19 @@ def algorithmic_bytes(ctx, p, acts_dev, mode, wbytes):
     return total + 8.0 * acts_dev.shape[0]
 
 
-def reward_kernel_name(ctx, p, mode, B, tmax):
+def reward_kernel_name(ctx, p, mode, B, tmax, dtype=None):
     """Which reward kernel the library picks for this call (mirrors eval_masks in spai_b200.cu)."""
-    k = ctx.info().max_row_slots
+    info = ctx.info()
+    k = info.max_row_slots
     if mode == "copy":
         if tmax * 40 <= p.num_edges:
             return "k3s_sparse_kernel"
-        return "k3t_lookup_kernel" if (k <= 8 and B >= 64) else "k3_copy_kernel"
+        if k <= 8 and B >= 64:
+            return "k3t_lookup_kernel"
+        if (dtype in ("f32", None) and 8 < k <= 32 and B >= 64 and not info.has_duplicates
+                and os.environ.get("SPAI_K3_MMA", "1") != "0"):
+            return "k3m_kernel(tcgen05)"
+        return "k3_copy_kernel"
     if k <= 8 and B >= 64:
         return "k3t_lookup_kernel(ls table)"
     return KNAMES[mode]
@@ -551,7 +557,7 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
             "ms_per_step": ms, "patterns_per_s": total / (ms / 1e3), "row_solves_per_s": total * p.n / (ms / 1e3),
             "per_rank_ms": per_rank,
             "kernel_share": {k: v / share_tot for k, v in ph.items()} if ph else None,
-            "reward_kernel": reward_kernel_name(ctx, p, mode, min(chunk, hi - lo), tmax_seen),
+            "reward_kernel": reward_kernel_name(ctx, p, mode, min(chunk, hi - lo), tmax_seen, dt),
             "compulsory_bytes_per_step": comp, "compulsory_frac_of_hbm_peak": comp / (ms / 1e3) / 1e9 / peak,
             "k0_valid_bytes_gbps": (k0_bytes_rank / (k0_ms_rank / 1e3) / 1e9) if k0_ms_rank else None,
             "k0_frac_of_hbm_peak_on_valid_bytes": (k0_bytes_rank / (k0_ms_rank / 1e3) / 1e9 / peak) if k0_ms_rank else None,
@@ -748,7 +754,7 @@ def run_b200_arm(args):
     k0_bytes = read_ids * 8 + float(B) * W * 4            # ids streamed once + the bitmask written once
     k0_bytes_padded = float(B) * T * 8 + float(B) * W * 4  # what a caller without row lengths makes K0 read
     peak, peak_src = measured_peak()
-    reward_kernel = reward_kernel_name(ctx, p, args.mode, B, T)
+    reward_kernel = reward_kernel_name(ctx, p, args.mode, B, T, args.dtype)
     mask_kernel = mask_kernel_name(p)
     info0 = ctx.info()
     rec_bytes = 16.0 * info0.contributions + 16.0 * p.n

@@ -990,6 +990,7 @@ static int ensure_plan(spai_ctx* c, int dtype, bool want_ls, cudaStream_t st) {
   // fp32 records always carry `a`; fp64 ls records are a second array
   SPAI_TRY(build_plan(c->plan_arena[dtype], c->P, c->hp, c->A, c->ha, dtype, want_ls || dtype == SPAI_F32,
                       c->plan[dtype], st));
+  SPAI_CUDA(cudaStreamSynchronize(st));            // one-time build (K1): plans are shared by every later call and stream
   c->plan_ready[dtype] = true;
   c->plan_has_ls[dtype] = want_ls || dtype == SPAI_F32;
   return SPAI_OK;
@@ -1069,6 +1070,7 @@ static int ensure_lut(spai_ctx* c, int dtype, cudaStream_t st) {
     plan.lut = t;
   }
   SPAI_CUDA(cudaGetLastError());
+  SPAI_CUDA(cudaStreamSynchronize(st));            // one-time build: a later call on another stream sees a finished table
   plan.bytes = ar.bytes;
   plan.lut_ready = true;
   return SPAI_OK;
@@ -1130,6 +1132,7 @@ static int ensure_lut_ls(spai_ctx* c, int dtype, cudaStream_t st) {
   else
     k3t_build_ls_kernel<double><<<(unsigned)plan.gram_count[0], K3T_ENTRIES, 0, st>>>(plan.gram[0], reinterpret_cast<double*>(t));
   SPAI_CUDA(cudaGetLastError());
+  SPAI_CUDA(cudaStreamSynchronize(st));            // one-time build: a later call on another stream sees a finished table
   plan.lut_ls = t;
   plan.bytes = ar.bytes;
   plan.lut_ls_ready = true;
