@@ -514,10 +514,13 @@ def side_config(name, args, rank, world, dev, local, flush, peak):
                 ph_acc[(mode, dt)] = phase_times(ctx, call, flush, 2)
             # the host-side trajectory generation leaves the GPU idle for seconds and its clocks drop to
             # idle (observed: one 32 ms call took 637 ms at 120 MHz): bring them back before timing
+            # (three 96-trajectory calls were not enough: at N = 2 two of one rank's nine cfg5 chunks measured 1.4x and 2.4x the
+            # others) -> one full untimed pass over the chunk, then the timed one
             warm = lambda: ctx.reward_batch(sub[:96], 0.5, mode, tdt, want=("reward",), lengths=sl[:96])
-            for _ in range(3):
+            for _ in range(2):
                 warm()
-                flush.zero_()
+            call()
+            flush.zero_()
             torch.cuda.synchronize()
             reps = 3 if not strong else 1
             ms = 0.0
@@ -683,6 +686,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local)
     numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tdtype = torch.float32 if args.dtype == "f32" else torch.float64
     wbytes = 4.0 if args.dtype == "f32" else 8.0
