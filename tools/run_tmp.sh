@@ -1,9 +1,10 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_k0b.py tests/test_gpu_fullsize.py tests/test_gpu_mma.py -x -q 2>&1 | tail -2
-for o in 0 1; do
-  echo "== overlap=$o cfg3"; SPAI_K0B_OVERLAP=$o timeout 300 python tools/ab_k0.py cfg3 1024 bucket 2>&1 | grep -E "int64\+len|int32" | cut -c1-200
-done
-for g in 64 128 256; do echo "== overlap group=$g cfg3"; SPAI_K0B_GROUP=$g timeout 300 python tools/ab_k0.py cfg3 1024 bucket 2>&1 | grep -E "int64\+len" | cut -c1-200; done
-for o in 0 1; do
-  echo "== overlap=$o cfg4"; SPAI_K0B_OVERLAP=$o timeout 300 python tools/ab_k0.py cfg4 1024 bucket 2>&1 | grep -E "int64\+len" | cut -c1-200
-done
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -12
+timeout 900 python bench.py --steps 5 --no-e2e --no-extras --cpu-sample 4 > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2l_bench.json'))
+for n,c in d['configs'].items():
+    print(n, {k:(round(v,3) if isinstance(v,float) else v) for k,v in c.get('sample_to_reward(K4g taken-bitmask, no id lists)',{}).items()})
+    for vn,v in c['variants'].items(): print('   ',vn, round(v['ms_per_step'],2), round(v['patterns_per_s']))
+PY
