@@ -708,6 +708,22 @@ def run_b200_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # cpu_baseline (rank 0, N = 1), same convention as the reference arm: the port on ALL host cores, bounded sample, with the
+    # single-core figure next to it. Measured BEFORE this process creates its CUDA context (the pool forks).
+    cpu_pre = None
+    if rank == 0 and world == 1:
+        procs = max(1, min(os.cpu_count() or 1, 64))
+        n1 = max(2, min(args.cpu_sample, 32))
+        v1, dt1 = cpu_port_throughput(args.config, args.scale, n1, 1)
+        if procs > 1 and args.cpu_sample >= 8:
+            nall = max(procs, min(4 * procs, 4 * args.cpu_sample))
+            v, dt = cpu_port_throughput(args.config, args.scale, nall, procs)
+        else:
+            v, dt, procs, nall = v1, dt1, 1, n1
+        cpu_pre = {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "single_core_value": v1,
+                   "sample": f"{nall} trajectories of the same workload, copy/fp32, numpy/scipy oracle port over {procs} processes "
+                             f"({dt:.1f} s); single process: {v1:.1f} patterns/s ({n1} trajectories, {dt1:.1f} s); "
+                             "`--impl reference` adds the staged reference itself"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = pin_to_gpu_numa_node(local) if world > 1 else None
@@ -977,18 +993,7 @@ def run_b200_arm(args):
                                          "sample": f"{rows_s.size} rows of one pattern, numpy.linalg.lstsq"}
         except Exception as exc:
             extras["ls_cpu_port/f64"] = {"error": str(exc)}
-        # same convention as the reference arm: the port on ALL host cores (one process per core, bounded sample), with the
-        # single-core figure next to it
-        procs = max(1, min(os.cpu_count() or 1, 64))
-        v1, dt1 = cpu_port_throughput(args.config, args.scale, max(2, min(args.cpu_sample, 32)), 1)
-        if procs > 1 and args.cpu_sample >= 8:
-            v, dt = cpu_port_throughput(args.config, args.scale, max(procs, min(4 * procs, 4 * args.cpu_sample)), procs)
-        else:
-            v, dt, procs = v1, dt1, 1
-        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "single_core_value": v1,
-               "sample": f"{max(procs, min(4 * procs, 4 * args.cpu_sample)) if procs > 1 else max(2, min(args.cpu_sample, 32))} trajectories of the "
-                         f"same workload, copy/fp32, numpy/scipy oracle port over {procs} processes ({dt:.1f} s); single process: "
-                         f"{v1:.1f} patterns/s ({dt1:.1f} s); `--impl reference` adds the staged reference itself"}
+        cpu = cpu_pre
 
     sampler_res = None
     if rank == 0 and world == 1 and not args.no_extras and not args.no_sampler:
