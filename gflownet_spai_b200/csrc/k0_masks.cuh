@@ -195,6 +195,41 @@ k0_transpose_kernel(const uint32_t* __restrict__ mask, int64_t B, int64_t W,
   }
 }
 
+// The same transpose on 64 x 64 tiles with 16-byte accesses on both sides (W % 4 == 0): four independent 16-byte loads in
+// flight per thread instead of four 4-byte ones, 256-byte segments per row on both sides.
+__global__ void __launch_bounds__(256)
+k0_transpose64_kernel(const uint32_t* __restrict__ mask, int64_t B, int64_t W,
+                      uint32_t* __restrict__ maskT, int64_t Bp) {
+  __shared__ uint32_t tile[64][65];
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;        // 16 x 16 threads, 4 columns each
+  const int64_t w0 = (int64_t)blockIdx.x * 64, b0 = (int64_t)blockIdx.y * 64;
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t b = b0 + r0 + 16 * i, w = w0 + c4;
+    if (w + 3 < W && b < B) v[i] = *reinterpret_cast<const uint4*>(mask + b * W + w);
+    else {
+      uint32_t t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (w + j < W) ? ((b < B) ? mask[b * W + w + j] : 0xffffffffu) : 0u;
+      v[i] = make_uint4(t[0], t[1], t[2], t[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t* dst = &tile[r0 + 16 * i][c4];
+    dst[0] = v[i].x; dst[1] = v[i].y; dst[2] = v[i].z; dst[3] = v[i].w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int wr = r0 + 16 * i;
+    const int64_t w = w0 + wr, b = b0 + c4;
+    if (w < W && b + 3 < Bp)
+      *reinterpret_cast<uint4*>(maskT + w * Bp + b) = make_uint4(tile[c4][wr], tile[c4 + 1][wr], tile[c4 + 2][wr], tile[c4 + 3][wr]);
+  }
+}
+
 // nnz(M) per trajectory = kept slots, minus the surplus of repeated coordinates
 // (coalesce() merges them, preconditioner.py:71 counts stored entries).
 __global__ void __launch_bounds__(256)

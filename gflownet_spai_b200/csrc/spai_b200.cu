@@ -633,8 +633,14 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
   bool use_lut = mode == SPAI_MODE_COPY && !sparse && plan.lut_ready && plan.tables_on && W > 0;
   if (const char* v = getenv("SPAI_K3_LUT")) use_lut = use_lut && atoi(v) != 0;               // A/B switch
   if (W > 0 && !sparse) {
-    const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
-    k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
+    static const bool t32 = [] { const char* e = getenv("SPAI_K0_TRANSPOSE"); return e && atoi(e) == 32; }();    // A/B: the 32 x 32 version
+    if (!t32 && (W & 3) == 0 && (Bp & 63) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(maskT) & 15) == 0) {
+      const dim3 tg((unsigned)ceil_div(W, 64), (unsigned)(Bp / 64));
+      k0_transpose64_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
+    } else {
+      const dim3 tg((unsigned)ceil_div(W, 32), (unsigned)(Bp / 32));
+      k0_transpose_kernel<<<tg, 256, 0, st>>>(mask, Bc, W, maskT, Bp);
+    }
     SPAI_CUDA(cudaGetLastError()); ++nl;
   }
   // K3s reads every mask word anyway: over the full row range it also counts the kept slots
