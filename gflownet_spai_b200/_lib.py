@@ -30,7 +30,7 @@ EXPORTS = [
     "spai_reward_batch_host_len", "spai_reward_batch_dev_len",
     "spai_ingest_coo_to_csr_dev", "spai_ingest_spgemm_count_dev", "spai_ingest_spgemm_fill_dev",
     "spai_ingest_superset_dev", "spai_ingest_neumann_dev", "spai_ingest_csr_drop_zeros_dev",
-    "spai_sample_taken_dev", "spai_sample_order_dev", "spai_sample_steps_dev",
+    "spai_sample_taken_dev", "spai_sample_order_dev", "spai_sample_steps_dev", "spai_ctx_k3m_rows",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     lib.spai_sample_order_dev.argtypes = [i32, pv, i64, i64, C.c_uint64, i64, pv, pv, i32, i64, pv]
     lib.spai_sample_steps_dev.argtypes = [i32, pv, i64, i64, pv, i64, pv, pv, C.c_uint64, i64, i64, i64, pv, i32, pv, i64,
                                           pv, pv]
+    lib.spai_ctx_k3m_rows.argtypes = [pv, p64, p64]
     lib.spai_ctx_set_deletion_hint.argtypes = [pv, i64]
     lib.spai_ctx_enable_timing.argtypes = [pv, i32]
     lib.spai_ctx_last_timing.argtypes = [pv, C.POINTER(SpaiTiming)]

@@ -15,6 +15,7 @@
 // accumulators (tcgen05.ld 32x32b), subtracts v and adds N squares.
 //
 // Warp-specialised CTA (288 threads), rows flow through three mbarrier rings without a block barrier:
+//   (row_lo / row_hi index the CLASS's row list: rows with <= 16 candidates and rows with 17..32 are separate launches)
 //   warps 4-7  producers: kept-mask words (cp.async into a private shared-memory window, two chunks of 8
 //              words in flight) -> the row's k bits -> bf16 pairs (one 64-bit multiply per 4 bits) -> tcgen05.st
 //   warp 8     one thread: cp.async.bulk of the record stages, tcgen05.mma issue, tcgen05.commit
@@ -77,14 +78,16 @@ __host__ __device__ constexpr int k3m_tmem_cols() {           // accumulator rin
 template <int N, int NSPLIT>
 __global__ void __launch_bounds__(128)
 k3m_build_kernel(const Rec32* __restrict__ recs, const int64_t* __restrict__ cptr, const int32_t* __restrict__ c_col,
-                 const RowHdr* __restrict__ rhdr, int64_t n, unsigned char* __restrict__ out) {
+                 const RowHdr* __restrict__ rhdr, const int32_t* __restrict__ rows, int64_t n, unsigned char* __restrict__ out,
+                 int2* __restrict__ hdr_out) {
   using Geo = K3mGeom<N, NSPLIT>;
   constexpr int KP = Geo::KP;
   constexpr int LD = 33, AUG = 32;
   __shared__ double Gs[4][LD * LD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * 4 + warp;
-  if (row >= n) return;
+  const int64_t idx_row = (int64_t)blockIdx.x * 4 + warp;      // position in the class's row list
+  if (idx_row >= n) return;
+  const int64_t row = rows[idx_row];
   double* G = Gs[warp];
   const RowHdr h = rhdr[row];
   const int k = h.k < N ? h.k : N;                             // the host only builds when max_k <= N
@@ -125,7 +128,7 @@ k3m_build_kernel(const Rec32* __restrict__ recs, const int64_t* __restrict__ cpt
   vv *= vv;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
-  unsigned char* o = out + row * (int64_t)Geo::RB;
+  unsigned char* o = out + idx_row * (int64_t)Geo::RB;
   for (int idx = lane; idx < N * KP; idx += 32) {
     const int nn = idx / KP, kk = idx % KP;                    // B[nn][kk] = L[kk][nn]
     double x = 0.0;
@@ -144,6 +147,7 @@ k3m_build_kernel(const Rec32* __restrict__ recs, const int64_t* __restrict__ cpt
     t.c = (float)(c > 0.0 ? c : 0.0);
     t.sp = h.sp; t.k = k; t.pad = 0;
     *reinterpret_cast<K3mTail*>(o + NSPLIT * Geo::TILE_B) = t;
+    hdr_out[idx_row] = make_int2(h.sp, k);
   }
   float* vout = reinterpret_cast<float*>(o + NSPLIT * Geo::TILE_B + 16);
   if (lane < N) vout[lane] = lane < k ? (float)G[AUG * LD + lane] : 0.f;
@@ -216,7 +220,7 @@ __device__ __forceinline__ void k3m_cp4(void* dst, const void* src) {
 
 template <int N, int NSPLIT, int NTM>
 __global__ void __launch_bounds__(K3M_THREADS, 2)
-k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rhdr, const uint32_t* __restrict__ maskT,
+k3m_kernel(const unsigned char* __restrict__ recs, const int2* __restrict__ rhdr, const uint32_t* __restrict__ maskT,
            int64_t Bp, int64_t W, double* __restrict__ partial, int row_lo, int row_hi, int dbg) {
   using Geo = K3mGeom<N, NSPLIT>;
   constexpr int KP = Geo::KP, RPS = Geo::RPS, NA = k3m_depth<N, NTM>(), NACC = NA;
@@ -318,7 +322,7 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    int64_t wb = nrows > 0 ? (int64_t)(__ldg(&rhdr[r0].sp) >> 5) : 0;
+    int64_t wb = nrows > 0 ? (int64_t)(__ldg(&rhdr[r0].x) >> 5) : 0;
     int cur = 0;
     fetch(0, wb);
     fetch(1, wb + K3M_MW);
@@ -328,14 +332,21 @@ k3m_kernel(const unsigned char* __restrict__ recs, const RowHdr* __restrict__ rh
     const int lane = tid & 31;
     auto hload = [&](int blk) {
       const int i = blk * 32 + lane;
-      return i < nrows ? __ldg(reinterpret_cast<const int4*>(rhdr + r0 + i)) : make_int4(0, 0, 0, 0);
+      return i < nrows ? __ldg(rhdr + r0 + i) : make_int2(0, 0);
     };
-    int4 hcur = hload(0), hnext = hload(1);
+    int2 hcur = hload(0), hnext = hload(1);
     for (int it = 0; it < nrows; ++it) {
       if (it && (it & 31) == 0) { hcur = hnext; hnext = hload((it >> 5) + 1); }
-      const int sp = __shfl_sync(0xffffffffu, hcur.y, it & 31), k = __shfl_sync(0xffffffffu, hcur.z, it & 31);
+      const int sp = __shfl_sync(0xffffffffu, hcur.x, it & 31), k = __shfl_sync(0xffffffffu, hcur.y, it & 31);
       const int64_t wd = sp >> 5;
-      while (wd - wb >= K3M_MW) {                                       // the row's two words must lie in [wb, wb + MW]
+      if (wd - wb >= 2 * K3M_MW) {                                      // far jump (sparse row class): re-base both buffers
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        wb = wd;
+        cur = 0;
+        fetch(0, wb);
+        fetch(1, wb + K3M_MW);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else if (wd - wb >= K3M_MW) {                                   // the row's two words must lie in [wb, wb + MW]
         wb += K3M_MW;
         cur ^= 1;
         fetch(cur ^ 1, wb + K3M_MW);                                    // the buffer just left is free (only this thread reads it)

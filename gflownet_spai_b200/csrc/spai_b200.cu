@@ -712,18 +712,24 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     SPAI_CUDA(cudaGetLastError()); ++nl;
     parts = gx;
   } else if (mode == SPAI_MODE_COPY && dtype == SPAI_F32 && plan.mma_ready && plan.tables_on && k3m_on() && Bc >= 64) {
-    // tensor-core row residuals (K3m): one wave of CTAs over (row ranges) x (128 * NTM trajectories)
-    const int64_t rows = row_hi - row_lo;
-    const int ntm_max = std::min(s.nt, 4);
-    int ntm = ntm_max;
-    if (const char* v = getenv("SPAI_K3M_NTM")) ntm = std::max(1, std::min(ntm_max, atoi(v)));      // A/B switch
-    if (ntm == 3) ntm = 2;
-    if (plan.mma_n == 32 && ntm > 2) ntm = 2;                 // 512 TMEM columns: up to 96 + 16 per (row, tile) at N = 32
-    const int gy = (int)(Bp / ((int64_t)128 * ntm));
-    int gx = 1;
-    const void* fn = nullptr;
-    size_t smem = 0;
-    int tcols = 512;
+    // tensor-core row residuals (K3m): per row class (<= 16 candidates: N = 16; 17..32: N = 32) one wave of CTAs over
+    // (ranges of the class's row list) x (128 * NTM trajectories)
+    int off = 0;
+    for (int cl = 0; cl < 2; ++cl) {
+      const auto& rl = plan.mma_rows_host[cl];
+      const int64_t i_lo = std::lower_bound(rl.begin(), rl.end(), (int32_t)row_lo) - rl.begin();
+      const int64_t i_hi = std::lower_bound(rl.begin(), rl.end(), (int32_t)std::min<int64_t>(row_hi, INT32_MAX)) - rl.begin();
+      const int64_t rows = i_hi - i_lo;
+      if (rows <= 0) continue;
+      const int n_cl = cl ? 32 : 16;
+      int ntm = std::min(s.nt, 4);
+      if (const char* v = getenv("SPAI_K3M_NTM")) ntm = std::max(1, std::min(ntm, atoi(v)));      // A/B switch
+      if (ntm == 3) ntm = 2;
+      if (n_cl == 32 && ntm > 2) ntm = 2;                     // TMEM columns / registers at N = 32
+      const int gy = (int)(Bp / ((int64_t)128 * ntm));
+      const void* fn = nullptr;
+      size_t smem = 0;
+      int tcols = 512;
 #define SPAI_K3M_PICK(N_, S_, NTM_)                                                      \
   do { fn = (const void*)k3m_kernel<N_, S_, NTM_>; smem = (size_t)k3m_smem_bytes<N_, S_, NTM_>(); tcols = k3m_tmem_cols<N_, NTM_>(); } while (0)
 #define SPAI_K3M_CLASS(N_)                                                               \
@@ -731,47 +737,44 @@ static int eval_masks(const Pattern& P, const Plan& plan, int mode, int dtype, c
     if (plan.mma_split == 2) { if (ntm == 2) SPAI_K3M_PICK(N_, 2, 2); else SPAI_K3M_PICK(N_, 2, 1); } \
     else { if (ntm == 2) SPAI_K3M_PICK(N_, 3, 2); else SPAI_K3M_PICK(N_, 3, 1); }                       \
   } while (0)
-    if (plan.mma_n == 16 && ntm >= 4) {
-      if (plan.mma_split == 2) SPAI_K3M_PICK(16, 2, 4); else SPAI_K3M_PICK(16, 3, 4);
-    } else if (plan.mma_n == 16) SPAI_K3M_CLASS(16);
-    else SPAI_K3M_CLASS(32);
+      if (n_cl == 16 && ntm >= 4) {
+        if (plan.mma_split == 2) SPAI_K3M_PICK(16, 2, 4); else SPAI_K3M_PICK(16, 3, 4);
+      } else if (n_cl == 16) SPAI_K3M_CLASS(16);
+      else SPAI_K3M_CLASS(32);
 #undef SPAI_K3M_CLASS
 #undef SPAI_K3M_PICK
-    SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, K3M_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
-    const int occ_api = per_sm;
-    {                                             // resident CTAs from the kernel's own resources (the occupancy API answered 1
-      cudaFuncAttributes fa;                      // for a 288-thread, 70 KB, 70-register kernel on this driver)
-      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) {
-        const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * ((K3M_THREADS + 31) / 32 * 32));
-        const int by_smem = (int)((227 * 1024) / (smem + 1024));
-        per_sm = std::max(1, std::min({by_regs, by_smem, 2048 / K3M_THREADS}));
-      } else cudaGetLastError();
-    }
-    per_sm = std::max(1, std::min(per_sm, 512 / tcols));                          // TMEM columns per SM
-    if (getenv("SPAI_K3M_VERBOSE"))
-      fprintf(stderr, "[k3m] N=%d split=%d ntm=%d smem=%zu tmem_cols=%d occupancy(api)=%d ctas/SM=%d gy=%d gx=%d\n", plan.mma_n,
-              plan.mma_split, ntm, smem, tcols, occ_api, per_sm, gy, (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)s.parts})));
-    if (rows > 0)
-      gx = (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)s.parts}));
-    if (rows <= 0) {
-      SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st));
-    } else {
-      const unsigned char* recp = plan.mma_rec;
-      int rlo = (int)row_lo, rhi = (int)row_hi;
+      SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SPAI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      int per_sm = 1;
+      {                                           // resident CTAs from the kernel's own resources (the occupancy API answered 1
+        cudaFuncAttributes fa;                    // for a 288-thread, 63 KB, 70-register kernel on this driver)
+        if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) {
+          const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * ((K3M_THREADS + 31) / 32 * 32));
+          const int by_smem = (int)((227 * 1024) / (smem + 1024));
+          per_sm = std::max(1, std::min({by_regs, by_smem, 2048 / K3M_THREADS}));
+        } else cudaGetLastError();
+      }
+      per_sm = std::max(1, std::min(per_sm, 512 / tcols));                        // TMEM columns per SM
+      const int room = std::max(1, s.parts - off);
+      const int gx = (int)std::max<int64_t>(1, std::min<int64_t>({ceil_div(rows, 32), (int64_t)std::max(1, sm_count * per_sm / gy), (int64_t)room}));
+      if (getenv("SPAI_K3M_VERBOSE"))
+        fprintf(stderr, "[k3m] class N=%d rows=%lld split=%d ntm=%d smem=%zu tmem_cols=%d ctas/SM=%d grid=(%d,%d)\n", n_cl, (long long)rows,
+                plan.mma_split, ntm, smem, tcols, per_sm, gx, gy);
+      const unsigned char* recp = plan.mma_rec[cl];
+      const int2* rh = plan.mma_hdr[cl];
+      int rlo = (int)i_lo, rhi = (int)i_hi;
       int64_t bp_ = Bp, w_ = W;
       const uint32_t* mt = maskT;
-      double* pp = partial;
-      const RowHdr* rh = plan.rhdr;
+      double* pp = partial + (int64_t)off * Bp;
       int dbg = 0;
       if (const char* v = getenv("SPAI_K3M_DEBUG")) dbg = atoi(v);                // timing experiments only (results are wrong)
       void* args[] = {(void*)&recp, (void*)&rh, (void*)&mt, (void*)&bp_, (void*)&w_, (void*)&pp, (void*)&rlo, (void*)&rhi, (void*)&dbg};
       SPAI_CUDA(cudaLaunchKernel(fn, dim3(gx, gy), dim3(K3M_THREADS), args, smem, st));
+      SPAI_CUDA(cudaGetLastError()); ++nl;
+      off += gx;
     }
-    SPAI_CUDA(cudaGetLastError()); ++nl;
-    parts = gx;
+    if (off == 0) { SPAI_CUDA(cudaMemsetAsync(partial, 0, (size_t)Bp * 8, st)); off = 1; }
+    parts = off;
   } else if (mode == SPAI_MODE_COPY) {
     // tiles that intersect [row_lo, row_hi)
     const auto& tr = plan.tile_row_host;
@@ -1098,24 +1101,35 @@ static int ensure_mma(spai_ctx* c, int dtype, cudaStream_t st) {
   if (plan.mma_ready || plan.mma_unavailable || dtype != SPAI_F32) return SPAI_OK;
   const int64_t n = c->P.n;
   const int split = k3m_split();
-  if (n == 0 || c->P.ndup || c->P.max_k > 32 || !plan.c_col || !plan.rec_copy) { plan.mma_unavailable = true; return SPAI_OK; }
-  const int N = c->P.max_k <= 16 ? 16 : 32;
-  const int64_t rb = N == 16 ? (split == 2 ? K3mGeom<16, 2>::RB : K3mGeom<16, 3>::RB)
-                             : (split == 2 ? K3mGeom<32, 2>::RB : K3mGeom<32, 3>::RB);
-  if (n * rb > ((int64_t)24 << 30)) { plan.mma_unavailable = true; return SPAI_OK; }
+  if (n == 0 || c->P.ndup || c->P.max_k > 32 || !plan.c_col || !plan.rec_copy || (int64_t)c->hp.sptr.size() != n + 1) { plan.mma_unavailable = true; return SPAI_OK; }
+  std::vector<int32_t> rows[2];
+  for (int64_t i = 0; i < n; ++i) rows[(c->hp.sptr[i + 1] - c->hp.sptr[i]) > 16 ? 1 : 0].push_back((int32_t)i);
+  const int64_t rb[2] = {split == 2 ? K3mGeom<16, 2>::RB : K3mGeom<16, 3>::RB, split == 2 ? K3mGeom<32, 2>::RB : K3mGeom<32, 3>::RB};
+  if ((int64_t)rows[0].size() * rb[0] + (int64_t)rows[1].size() * rb[1] > ((int64_t)24 << 30)) { plan.mma_unavailable = true; return SPAI_OK; }
   Arena& ar = c->plan_arena[dtype];
-  unsigned char* rec = nullptr;
-  SPAI_TRY(ar.alloc(&rec, n * rb));
   const Rec32* rc = reinterpret_cast<const Rec32*>(plan.rec_copy);
-  const unsigned blocks = (unsigned)ceil_div(n, 4);
-  if (N == 16 && split == 2) k3m_build_kernel<16, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
-  else if (N == 16) k3m_build_kernel<16, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
-  else if (split == 2) k3m_build_kernel<32, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
-  else k3m_build_kernel<32, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, n, rec);
-  SPAI_CUDA(cudaGetLastError());
-  SPAI_CUDA(cudaStreamSynchronize(st));            // one-time build: later calls on other streams see a finished table
-  plan.mma_rec = rec;
-  plan.mma_n = N;
+  for (int cl = 0; cl < 2; ++cl) {
+    const int64_t cnt = (int64_t)rows[cl].size();
+    plan.mma_count[cl] = cnt;
+    if (!cnt) continue;
+    unsigned char* rec = nullptr;
+    int2* hdr = nullptr;
+    int32_t* rdev = nullptr;
+    SPAI_TRY(ar.alloc(&rec, cnt * rb[cl]));
+    SPAI_TRY(ar.alloc(&hdr, cnt));
+    SPAI_TRY(ar.alloc(&rdev, cnt));
+    SPAI_CUDA(cudaMemcpyAsync(rdev, rows[cl].data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)ceil_div(cnt, 4);
+    if (cl == 0 && split == 2) k3m_build_kernel<16, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, rdev, cnt, rec, hdr);
+    else if (cl == 0) k3m_build_kernel<16, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, rdev, cnt, rec, hdr);
+    else if (split == 2) k3m_build_kernel<32, 2><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, rdev, cnt, rec, hdr);
+    else k3m_build_kernel<32, 3><<<blocks, 128, 0, st>>>(rc, plan.cptr, plan.c_col, plan.rhdr, rdev, cnt, rec, hdr);
+    SPAI_CUDA(cudaGetLastError());
+    SPAI_CUDA(cudaStreamSynchronize(st));          // one-time build (and rows[] is a host temporary)
+    plan.mma_rec[cl] = rec;
+    plan.mma_hdr[cl] = hdr;
+    plan.mma_rows_host[cl] = std::move(rows[cl]);
+  }
   plan.mma_split = split;
   plan.bytes = ar.bytes;
   plan.mma_ready = true;
@@ -1393,6 +1407,14 @@ int spai_ctx_set_workspace_limit(spai_ctx* c, int64_t bytes) {
 int spai_ctx_set_deletion_hint(spai_ctx* c, int64_t max_deletions) {
   if (!c || max_deletions < 0) return SPAI_ERR_INVALID;
   c->deletion_hint = max_deletions;
+  return SPAI_OK;
+}
+
+int spai_ctx_k3m_rows(const spai_ctx* c, int64_t* rows16, int64_t* rows32) {
+  if (!c || !rows16 || !rows32) { set_error("spai_ctx_k3m_rows: null argument"); return SPAI_ERR_INVALID; }
+  const Plan& p = c->plan[SPAI_F32];
+  *rows16 = p.mma_ready ? p.mma_count[0] : 0;
+  *rows32 = p.mma_ready ? p.mma_count[1] : 0;
   return SPAI_OK;
 }
 

@@ -157,8 +157,13 @@ struct Plan {
   // tensor-core copy kernel (K3m, fp32, rows with <= 32 candidates, no repeated coordinates; built on first use)
   bool mma_ready = false;
   bool mma_unavailable = false;
-  unsigned char* mma_rec = nullptr;                  // [n][K3mGeom::RB]
-  int mma_n = 0, mma_split = 0;                      // N = 16 (KP = 32) or 32 (KP = 48); bf16 terms per entry of L
+  // two row classes: [0] rows with <= 16 candidates (N = K = 16), [1] rows with 17..32 (N = K = 32); each class has its own
+  // sorted row list, contiguous records and compact headers {sp, k}
+  unsigned char* mma_rec[2] = {nullptr, nullptr};    // [count][K3mGeom::RB]
+  int2* mma_hdr[2] = {nullptr, nullptr};             // [count] {first slot, candidates}
+  int64_t mma_count[2] = {0, 0};
+  std::vector<int32_t> mma_rows_host[2];             // ascending row ids of the class
+  int mma_split = 0;                                 // bf16 terms per entry of L
   // deletion-driven copy kernel (K3s, built on first use)
   bool sparse_ready = false;
   bool sparse_unavailable = false;                   // a row of A or of the pattern exceeds the SlotMeta fields

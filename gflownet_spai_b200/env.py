@@ -124,6 +124,13 @@ class SpaiContext:
         no action list): short trajectories then take the deletion-driven kernel. 0 = unknown."""
         check(self._lib.spai_ctx_set_deletion_hint(self._h, int(max_deletions)), "set_deletion_hint")
 
+    def k3m_rows(self) -> tuple:
+        """(rows with <= 16 candidates, rows with 17..32) served by the tensor-core copy kernel; (0, 0) before its records
+        exist or when it does not apply (spai_ctx_k3m_rows)."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self._lib.spai_ctx_k3m_rows(self._h, C.byref(a), C.byref(b)), "spai_ctx_k3m_rows")
+        return int(a.value), int(b.value)
+
     def enable_timing(self, on: bool = True):
         check(self._lib.spai_ctx_enable_timing(self._h, int(on)), "enable_timing")
 

@@ -316,6 +316,11 @@ typedef struct spai_timing {
   double compulsory_bytes;  /* bytes that must cross HBM for the batch           */
   double h2d_bytes;         /* host->device bytes actually copied (host entry)   */
 } spai_timing;
+/* Rows served by the tensor-core copy kernel (K3m, k3m_mma.cuh) once its records exist (built by the first
+ * copy/fp32 call with >= 64 trajectories on a pattern without repeated coordinates and <= 32 candidates per row;
+ * preconditioner.py:79-93 is what it computes): rows with <= 16 candidates, rows with 17..32. Both 0 = the CUDA-core
+ * row sweep serves those calls. */
+int spai_ctx_k3m_rows(const spai_ctx* ctx, int64_t* rows16, int64_t* rows32);
 int spai_ctx_enable_timing(spai_ctx* ctx, int enable);
 int spai_ctx_last_timing(const spai_ctx* ctx, spai_timing* out);
 

@@ -56,6 +56,8 @@ def test_tensor_core_rows_match_row_sweep_and_oracle(cfg, scale, bsz, split):
         acts = _trajectories(p.num_edges, bsz, 17)
         t = torch.from_numpy(acts).cuda()
         got = ctx.reward_batch(t, 0.5, "copy", torch.float32)
+        r16, r32 = ctx.k3m_rows()
+        assert r16 + r32 == p.n and (r32 > 0) == (k > 16)         # the tensor-core records exist: the call above ran K3m
         with _env(SPAI_K3_MMA="0"):
             ref = ctx.reward_batch(t, 0.5, "copy", torch.float32)
     assert torch.equal(got["nnz_m"], ref["nnz_m"])
@@ -76,6 +78,7 @@ def test_tensor_core_rows_row_ranges_and_timing_label():
     ctx = _ctx(p)
     acts = torch.from_numpy(synth.make_trajectories(p.num_edges, 70, seed0=4)).cuda()
     full = ctx.reward_batch(acts, 0.3, "copy", torch.float32)
+    assert sum(ctx.k3m_rows()) == p.n
     tot = torch.zeros(70, dtype=torch.float64, device="cuda")
     for r in range(3):
         lo, hi = shard_bounds(p.n, 3, r)
@@ -115,6 +118,7 @@ def test_tensor_core_rows_semidefinite_and_zero_slots():
     acts = synth.make_trajectories(rows.size, 128, seed0=2)
     t = torch.from_numpy(acts).cuda()
     got = ctx.reward_batch(t, 0.5, "copy", torch.float32)
+    assert sum(ctx.k3m_rows()) == n
     with _env(SPAI_K3_MMA="0"):
         ref = ctx.reward_batch(t, 0.5, "copy", torch.float32)
     assert torch.allclose(got["residual"], ref["residual"], rtol=5e-6)
