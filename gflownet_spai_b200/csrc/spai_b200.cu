@@ -11,6 +11,7 @@
 
 #include "k0_masks.cuh"
 #include "k0b_bucket.cuh"
+#include "k0c_cluster.cuh"
 #include "k1_plan.cuh"
 #include "k2_ls.cuh"
 #include "k2g_gram.cuh"
@@ -1503,11 +1504,46 @@ static inline int k0b_threads(int64_t C) {
 static inline bool k0_fits_smem(int64_t W) { return W * 4 <= K0S_MAX_SMEM; }
 static inline int k0_variant() {             // A/B + test switch, read per call
   const char* e = getenv("SPAI_K0_VARIANT");
-  return !e ? 0 : (!strcmp(e, "red") ? 1 : (!strcmp(e, "smem") ? 2 : (!strcmp(e, "bucket") ? 3 : 0)));
+  return !e ? 0 : (!strcmp(e, "red") ? 1 : (!strcmp(e, "smem") ? 2 : (!strcmp(e, "bucket") ? 3 : (!strcmp(e, "cluster") ? 4 : 0))));
+}
+// K0c (k0c_cluster.cuh): one cluster per trajectory, the bitmask sliced over the CTAs' shared memory.
+// Smallest cluster whose slice + exchange buffers fit 227 KB; SPAI_K0C_CS / SPAI_K0C_GROUPS override (A/B, tests).
+struct K0cGeom { int cs = 0, spc = 0, cap = 0, nh = 2; size_t smem = 0; uint32_t inv = 0; };
+static bool k0c_geometry(const Pattern& P, K0cGeom* g) {
+  const int64_t C = ceil_div(P.E, (int64_t)1 << K0C_SEG_SHIFT);
+  const char* e = getenv("SPAI_K0C_GROUPS");
+  const int nh_forced = e ? atoi(e) : 0;
+  const char* f = getenv("SPAI_K0C_CS");
+  const int forced = f ? atoi(f) : 0;
+  // most groups first (their phases overlap), then the smallest cluster, then the roomiest inbox slot
+  for (int nh = 4; nh >= 1; --nh) {
+    if (nh_forced >= 1 && nh_forced <= 4 && nh != nh_forced) continue;
+    if (!(nh_forced >= 1 && nh_forced <= 4) && nh == 4) continue;          // default: at most 3 groups
+    for (int cs = 2; cs <= K0C_MAX_CS; ++cs) {
+      if (forced >= 2 && forced <= K0C_MAX_CS && cs != forced) continue;
+      const int64_t spc = ceil_div(C, (int64_t)cs);
+      for (double sig = 6.0; sig >= 4.0; sig -= 0.5) {
+        const int cap = k0c_cap(cs, sig);
+        const size_t smem = k0c_smem((int)spc, cs, cap, nh);
+        if (smem > (size_t)K0C_MAX_SMEM) continue;
+        g->cs = cs; g->spc = (int)spc; g->cap = cap; g->nh = nh; g->smem = smem;
+        g->inv = (uint32_t)((65536 + spc - 1) / spc);
+        return true;
+      }
+    }
+  }
+  return false;
+}
+static inline bool k0c_applies(const Pattern& P, int64_t T) {
+  // opt-in (SPAI_K0_VARIANT=cluster): measured on B200 at 6.4-6.7 ms per 1024 cfg3 trajectories against 3.87 ms for K0b
+  //  — ~90 instructions per id, mostly per-round bookkeeping amortised over 8 ids per thread
+  if (k0_variant() != 4 || T <= 0) return false;
+  K0cGeom g;
+  return k0c_geometry(P, &g);
 }
 // K0b applies when the bitmask exceeds one CTA's shared memory and the segment count fits the sort kernel
 static inline bool k0b_applies(const Pattern& P, int64_t T) {
-  if (k0_variant() == 1 || T <= 0) return false;
+  if (k0_variant() == 1 || T <= 0 || k0c_applies(P, T)) return false;
   const int64_t C = ceil_div(P.E, (int64_t)1 << K0B_SEG_SHIFT);
   if (C > K0B_MAX_SEGS) return false;
   return !k0_fits_smem(P.words()) || k0_variant() == 3;
@@ -1545,7 +1581,36 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
   const int32_t* eslot = P.identity_perm ? nullptr : P.edge_slot;
   const int64_t* a64 = reinterpret_cast<const int64_t*>(act);
   const int32_t* a32 = reinterpret_cast<const int32_t*>(act);
-  if (k0_fits_smem(W) && k0_variant() != 1 && k0_variant() != 3 && T > 0) {
+  if (k0c_applies(P, T)) {
+    K0cGeom g;
+    k0c_geometry(P, &g);
+    SPAI_CUDA(cudaMemsetAsync(nnz0, 0, (size_t)bc * 8, st));
+    if (bc * g.cs >= ((int64_t)1 << 31)) { set_error("batch too large for one launch"); return SPAI_ERR_UNSUPPORTED; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(bc * g.cs));
+    cfg.blockDim = dim3((unsigned)(g.nh * K0C_HT));
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)g.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    unsigned long long* nnzu = reinterpret_cast<unsigned long long*>(nnz0);
+#define SPAI_K0C_LAUNCH(IDT, PTR, MAP, NH)                                                                              \
+  do {                                                                                                                  \
+    SPAI_CUDA(cudaFuncSetAttribute(k0c_cluster_kernel<IDT, MAP, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+    SPAI_CUDA(cudaLaunchKernelEx(&cfg, k0c_cluster_kernel<IDT, MAP, NH>, PTR, T, act_ld, row_len, eslot, P.E, g.cs, g.spc, g.cap, \
+                                 g.inv, mask, W, nnzu));                                                                \
+  } while (0)
+#define SPAI_K0C_LAUNCH2(IDT, PTR, MAP) \
+  do { if (g.nh == 1) SPAI_K0C_LAUNCH(IDT, PTR, MAP, 1); else if (g.nh == 2) SPAI_K0C_LAUNCH(IDT, PTR, MAP, 2); else if (g.nh == 3) SPAI_K0C_LAUNCH(IDT, PTR, MAP, 3); else SPAI_K0C_LAUNCH(IDT, PTR, MAP, 4); } while (0)
+    if (elem == 8) { if (eslot) SPAI_K0C_LAUNCH2(int64_t, a64, true); else SPAI_K0C_LAUNCH2(int64_t, a64, false); }
+    else { if (eslot) SPAI_K0C_LAUNCH2(int32_t, a32, true); else SPAI_K0C_LAUNCH2(int32_t, a32, false); }
+#undef SPAI_K0C_LAUNCH2
+#undef SPAI_K0C_LAUNCH
+    ++*launches;
+    *nnz_fused = true;
+  } else if (k0_fits_smem(W) && k0_variant() != 1 && k0_variant() != 3 && T > 0) {
     if (elem == 8) {
       SPAI_CUDA(cudaFuncSetAttribute(k0_mask_build_smem_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0S_MAX_SMEM));
       k0_mask_build_smem_kernel<int64_t><<<(unsigned)bc, K0S_THREADS, (size_t)W * 4, st>>>(a64, bc, T, act_ld, eslot, P.E, mask, W, nnz0, row_len);

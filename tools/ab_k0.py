@@ -2,7 +2,7 @@
 (K0b) at several group sizes, with and without row lengths, int64 and int32 ids.
 
 Usage (GPU box): python tools/ab_k0.py [cfg] [batch] [variants,comma]
-  variant = red | bucket[:group] ; default: red,bucket,bucket:8,bucket:16,bucket:32,bucket:64,bucket:100000
+  variant = red | bucket[:group] | cluster[:cs[:groups]] ; default: red,bucket,bucket:8,bucket:16,bucket:32,bucket:64,bucket:100000
 Prints ms of the mask phase (CUDA events inside the library), GB/s on the VALID id bytes
 (sum T_b * 8 + B*W*4) and the fraction of the measured HBM peak; checks that every variant yields the
 same nnz(M) and rewards as the first one.
@@ -49,10 +49,16 @@ def main():
     for v in variants:
         name, _, grp = v.partition(":")
         os.environ["SPAI_K0_VARIANT"] = name
-        if grp:
+        for k in ("SPAI_K0B_GROUP", "SPAI_K0C_CS", "SPAI_K0C_GROUPS"):
+            os.environ.pop(k, None)
+        if name == "cluster" and grp:                      # cluster:<cs>:<groups>
+            cs, _, nh = grp.partition(":")
+            if cs and cs != "0":
+                os.environ["SPAI_K0C_CS"] = cs
+            if nh:
+                os.environ["SPAI_K0C_GROUPS"] = nh
+        elif grp:
             os.environ["SPAI_K0B_GROUP"] = grp
-        else:
-            os.environ.pop("SPAI_K0B_GROUP", None)
         for label, a_in, ln in (("int64+len", acts, lens), ("int64 padded", acts, None), ("int32+len", a32, lens)):
             if name == "red" and label == "int32+len":
                 continue
