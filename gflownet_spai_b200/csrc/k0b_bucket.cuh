@@ -36,8 +36,8 @@ constexpr int K0B_CHUNK_MAX = K0B_THREADS * K0B_IDS;
 constexpr int K0B_MAX_SEGS = 512;                       // E <= 33.5 M slots
 constexpr int K0B_R = 8;                                // segments per build CTA (64 KB of shared memory)
 
-inline size_t k0b_sort_smem(int C, int threads) {
-  return (size_t)(threads / 32) * (C + 1) * 4 + (size_t)threads * K0B_IDS * 2 + 128;
+inline size_t k0b_sort_smem(int C, int threads, int ids = K0B_IDS) {
+  return (size_t)(threads / 32) * (C + 1) * 4 + (size_t)threads * ids * 2 + 128;
 }
 
 // hdr u16[B][nchunks][C + 1]: hdr[..][s] = first position of segment s inside the sorted
@@ -45,13 +45,13 @@ inline size_t k0b_sort_smem(int C, int threads) {
 // are not written (pass 2 derives the same chunk count from the same length).
 // Straight-line code: every id takes the same path (ids that match no edge are counted in a
 // trash bucket C of the warp and never stored), the edge -> slot map is a template switch.
-template <typename IdT, bool HAS_MAP, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+template <typename IdT, bool HAS_MAP, int THREADS, int IDS = K0B_IDS>
+__global__ void __launch_bounds__(THREADS, (IDS == K0B_IDS ? 1024 : 1536) / THREADS)
 k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
                 const int32_t* __restrict__ row_len, const int32_t* __restrict__ edge_slot,
                 int64_t E, int C, uint16_t* __restrict__ stage, int64_t ld_stage,
                 uint16_t* __restrict__ hdr, int64_t nchunks) {
-  constexpr int NWARPS = THREADS / 32, CHUNK = THREADS * K0B_IDS;
+  constexpr int NWARPS = THREADS / 32, CHUNK = THREADS * IDS;
   extern __shared__ __align__(16) uint32_t k0b_sm[];
   const int C1 = C + 1;                                           // + trash bucket
   uint32_t* cnt = k0b_sm;                                         // [WARPS][C1] counters, then bases
@@ -67,13 +67,13 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   const IdT* row = actions + b * ld + c0;
   const int left = (int)min(len - c0, (int64_t)CHUNK);        // ids of this chunk
 
-  IdT v[K0B_IDS];
+  IdT v[IDS];
   if (left == CHUNK) {
 #pragma unroll
-    for (int u = 0; u < K0B_IDS; ++u) v[u] = __ldcs(row + u * THREADS + tid);
+    for (int u = 0; u < IDS; ++u) v[u] = __ldcs(row + u * THREADS + tid);
   } else {
 #pragma unroll
-    for (int u = 0; u < K0B_IDS; ++u) {
+    for (int u = 0; u < IDS; ++u) {
       const int t = u * THREADS + tid;
       v[u] = (t < left) ? __ldcs(row + t) : (IdT)-1;
     }
@@ -81,12 +81,12 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   for (int i = tid; i < NWARPS * C1; i += THREADS) cnt[i] = 0;
   __syncthreads();
 
-  uint32_t key[K0B_IDS];       // slot; 0xffffffff (segment = trash) for ids that match no edge
-  uint32_t pos[K0B_IDS];       // rank inside the (warp, segment) sub-list
+  uint32_t key[IDS];       // slot; 0xffffffff (segment = trash) for ids that match no edge
+  uint32_t pos[IDS];       // rank inside the (warp, segment) sub-list
   uint32_t* wc = cnt + warp * C1;
   const uint32_t Eu = (uint32_t)E;                                // E < 2^31 (checked at context creation)
 #pragma unroll
-  for (int u = 0; u < K0B_IDS; ++u) {
+  for (int u = 0; u < IDS; ++u) {
     bool ok;
     uint32_t lo;
     if (sizeof(IdT) == 8) {
@@ -144,7 +144,7 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   __syncthreads();
 
 #pragma unroll
-  for (int u = 0; u < K0B_IDS; ++u) {
+  for (int u = 0; u < IDS; ++u) {
     const uint32_t s = key[u];
     const uint32_t seg = min(s >> K0B_SEG_SHIFT, (uint32_t)C);
     const uint32_t at = wc[seg] + ((s == 0xffffffffu) ? 0u : pos[u]);
@@ -205,6 +205,213 @@ k0b_build_kernel(const uint16_t* __restrict__ stage, int64_t ld_stage, const uin
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (l[u] != 0xffffffffu) atomicAnd(seg + (l[u] >> 5), ~(1u << (l[u] & 31)));
+    }
+  }
+  __syncthreads();
+  long long cntv = 0;
+  uint32_t* out = mask + b * W + w0;
+  for (int w = tid; w < nw; w += K0B_THREADS) {
+    const uint32_t x = k0b_sm[w];
+    out[w] = x;
+    cntv += __popc(x);
+  }
+  for (int o = 16; o; o >>= 1) cntv += __shfl_xor_sync(0xffffffffu, cntv, o);
+  if (lane == 0) part[warp] = cntv;
+  __syncthreads();
+  if (tid == 0 && nnz) {
+    long long t = 0;
+    for (int i = 0; i < K0B_WARPS; ++i) t += part[i];
+    atomicAdd(nnz + b, (unsigned long long)t);
+  }
+}
+
+// Build pass, second version (ncu source view of the first, cfg3 B = 256: half of the samples wait on the four 2-byte
+// loads a lane has in flight, and every shared-memory atomic drags five address instructions along). Same task
+// decomposition; a lane group now reads its run as aligned 8-byte words (four ids per load, up to four loads = the whole
+// run of a cfg3 chunk in flight), the loads of the warp's NEXT chunk are issued before the bits of the current one are
+// cleared, and bits are cleared by red.shared on a 32-bit shared address.
+__device__ __forceinline__ void k0b_red_and(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 k0b_ldg8(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+// L = lanes per (chunk, segment) run: a warp-iteration covers 4 / L chunks (32 lanes = 8 segments x L lanes x 4 / L
+// chunks), so the per-iteration bookkeeping is spread over 4 / L times the ids when runs are short (L = 4: runs of
+// >= 48 ids, cfg3; L = 2: cfg4, cfg5).
+template <int L>
+__global__ void __launch_bounds__(K0B_THREADS)
+k0b_build2_kernel(const uint16_t* __restrict__ stage, int64_t ld_stage, const uint16_t* __restrict__ hdr,
+                  int64_t nchunks, int C, const int32_t* __restrict__ row_len, int64_t T, int64_t E,
+                  uint32_t* __restrict__ mask, int64_t W, unsigned long long* __restrict__ nnz,
+                  int tasks_per_b, int chunk_ids) {
+  extern __shared__ __align__(16) uint32_t k0b_sm[];
+  __shared__ long long part[K0B_WARPS];
+  constexpr int CPI = 4 / L;                                         // chunks per warp-iteration
+  const int64_t b = blockIdx.x / tasks_per_b;
+  const int task = (int)(blockIdx.x % tasks_per_b);
+  const int seg0 = task * K0B_R;
+  const int nseg = min(K0B_R, C - seg0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t w0 = (int64_t)seg0 * K0B_SEG_WORDS;
+  const int nw = (int)min((int64_t)nseg * K0B_SEG_WORDS, W - w0);   // words of this slice
+  const uint32_t tail = (E & 31) ? ((1u << (E & 31)) - 1u) : 0xffffffffu;
+  for (int w = tid; w < nw; w += K0B_THREADS) k0b_sm[w] = (w0 + w == W - 1) ? tail : 0xffffffffu;
+  __syncthreads();
+  int64_t len = T;
+  if (row_len) len = min(T, (int64_t)row_len[b]);
+  const int nch = (int)((len + chunk_ids - 1) / chunk_ids);
+  static_assert(K0B_R == 8, "lane groups assume 8 segments per build CTA");
+  const int sub = lane % L, grp = (lane / L) & 7, cj = lane / (8 * L);
+  const bool live = grp < nseg;                                      // segments beyond the pattern have no shared memory
+  const uint32_t seg_addr = (uint32_t)__cvta_generic_to_shared(k0b_sm + grp * K0B_SEG_WORDS);
+  const int C1 = C + 1, cw = chunk_ids >> 2;
+  const uint16_t* hb = hdr + b * nchunks * (int64_t)C1 + seg0 + grp;                      // + chunk * C1
+  const uint2* sb = reinterpret_cast<const uint2*>(stage + b * ld_stage);                  // + chunk * cw
+  constexpr int CSTEP = K0B_WARPS * CPI;
+
+  // clear the bits of one 8-byte word (ids at chunk positions 4q .. 4q+3; valid inside [start, end)): straight-line
+  // code, the atomic of an id outside the run is predicated off
+  auto clear4 = [&](const uint2& v, int q, int start, int end) {
+    const uint32_t span = (uint32_t)(end - start);
+    const uint32_t t = (uint32_t)(4 * q - start);                   // sub-position i is valid iff t + i < span (unsigned)
+    const uint32_t id[4] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.and.b32 [%2], %3;\n\t}" ::"r"(t + (uint32_t)i),
+                   "r"(span), "r"(seg_addr + ((id[i] >> 3) & 0x1ffcu)), "r"(~(1u << (id[i] & 31u)))
+                   : "memory");
+  };
+  auto header = [&](int c, int& start, int& end) {                  // the lane's own run bounds: two adjacent 16-bit entries
+    start = 0; end = 0;
+    if (live && c < nch) {
+      start = (int)__ldg(hb + (int64_t)c * C1);
+      end = (int)__ldg(hb + (int64_t)c * C1 + 1);
+    }
+  };
+  auto fetch = [&](int c, int start, int end, uint2 (&v)[4]) {
+    const uint2* src = sb + (int64_t)c * cw;
+    const int q = (start >> 2) + sub, q1 = (end + 3) >> 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (q + L * u < q1) ? k0b_ldg8(src + q + L * u) : make_uint2(0u, 0u);
+  };
+
+  int c = warp * CPI + cj;
+  int start, end, nstart, nend;
+  uint2 cur[4];
+  header(c, start, end);
+  header(c + CSTEP, nstart, nend);
+  fetch(c, start, end, cur);
+  for (int cb = warp * CPI; cb < nch; cb += CSTEP) {                 // warp-uniform
+    // the next iteration's words fly while this one's bits are cleared; the header after that one is fetched too
+    uint2 nxt[4];
+    fetch(c + CSTEP, nstart, nend, nxt);
+    int n2s, n2e;
+    header(c + 2 * CSTEP, n2s, n2e);
+
+    const uint2* src = sb + (int64_t)c * cw;
+    const int q = (start >> 2) + sub, q1 = (end + 3) >> 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (q + L * u < q1) clear4(cur[u], q + L * u, start, end);
+    for (int qq = q + 4 * L; qq < q1; qq += L) clear4(k0b_ldg8(src + qq), qq, start, end);   // longer runs: not pipelined
+
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    start = nstart; end = nend;
+    nstart = n2s; nend = n2e;
+    c += CSTEP;
+  }
+  __syncthreads();
+  long long cntv = 0;
+  uint32_t* out = mask + b * W + w0;
+  for (int w = tid; w < nw; w += K0B_THREADS) {
+    const uint32_t x = k0b_sm[w];
+    out[w] = x;
+    cntv += __popc(x);
+  }
+  for (int o = 16; o; o >>= 1) cntv += __shfl_xor_sync(0xffffffffu, cntv, o);
+  if (lane == 0) part[warp] = cntv;
+  __syncthreads();
+  if (tid == 0 && nnz) {
+    long long t = 0;
+    for (int i = 0; i < K0B_WARPS; ++i) t += part[i];
+    atomicAdd(nnz + b, (unsigned long long)t);
+  }
+}
+
+// Build pass, third version: a LANE owns the run of one (chunk, segment) pair. Warp w of the CTA takes segment w & 7 of
+// the task and 32 chunks at a time (warps 0-7 the even blocks of 32 chunks, warps 8-15 the odd ones); every lane reads
+// its run — contiguous in its chunk — as aligned 16-byte words (8 ids), up to four in flight, while the next block's two
+// header entries are already being fetched. No lane waits on a short run of its neighbours' chunk and the per-chunk work
+// of versions 1 and 2 (nine header entries, shuffles and bound checks per 4096 / C * 8 ids) is gone: what remains per run
+// is two header loads and the word loop. Short runs (cfg4: 32 ids, cfg5: 24 ids per chunk and segment) gain most.
+__device__ __forceinline__ uint4 k0b_ldg16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__global__ void __launch_bounds__(K0B_THREADS)
+k0b_build3_kernel(const uint16_t* __restrict__ stage, int64_t ld_stage, const uint16_t* __restrict__ hdr,
+                  int64_t nchunks, int C, const int32_t* __restrict__ row_len, int64_t T, int64_t E,
+                  uint32_t* __restrict__ mask, int64_t W, unsigned long long* __restrict__ nnz,
+                  int tasks_per_b, int chunk_ids) {
+  extern __shared__ __align__(16) uint32_t k0b_sm[];
+  __shared__ long long part[K0B_WARPS];
+  const int64_t b = blockIdx.x / tasks_per_b;
+  const int task = (int)(blockIdx.x % tasks_per_b);
+  const int seg0 = task * K0B_R;
+  const int nseg = min(K0B_R, C - seg0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t w0 = (int64_t)seg0 * K0B_SEG_WORDS;
+  const int nw = (int)min((int64_t)nseg * K0B_SEG_WORDS, W - w0);   // words of this slice
+  const uint32_t tail = (E & 31) ? ((1u << (E & 31)) - 1u) : 0xffffffffu;
+  for (int w = tid; w < nw; w += K0B_THREADS) k0b_sm[w] = (w0 + w == W - 1) ? tail : 0xffffffffu;
+  __syncthreads();
+  int64_t len = T;
+  if (row_len) len = min(T, (int64_t)row_len[b]);
+  const int nch = (int)((len + chunk_ids - 1) / chunk_ids);
+  static_assert(K0B_R == 8 && K0B_WARPS == 16, "warp -> (segment, chunk block parity) map");
+  const int g = warp & 7, half = warp >> 3;
+  if (g < nseg) {
+    const uint32_t seg_addr = (uint32_t)__cvta_generic_to_shared(k0b_sm + g * K0B_SEG_WORDS);
+    const int C1 = C + 1, cw = chunk_ids >> 3;
+    const uint16_t* hb = hdr + b * nchunks * (int64_t)C1 + seg0 + g;
+    const uint4* sb = reinterpret_cast<const uint4*>(stage + b * ld_stage);
+    auto clear8 = [&](const uint4& v, int q, int start, int end) {
+      const int lo = start - 8 * q, hi = end - 8 * q;                // valid sub-positions: lo <= i < hi
+      const uint32_t id[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+      if (lo <= 0 && hi >= 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) k0b_red_and(seg_addr + ((id[i] >> 3) & 0x1ffcu), ~(1u << (id[i] & 31u)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i >= lo && i < hi) k0b_red_and(seg_addr + ((id[i] >> 3) & 0x1ffcu), ~(1u << (id[i] & 31u)));
+      }
+    };
+    int c = half * 32 + lane;
+    int o0 = 0, o1 = 0;
+    if (c < nch) { o0 = (int)__ldg(hb + (int64_t)c * C1); o1 = (int)__ldg(hb + (int64_t)c * C1 + 1); }
+    for (int cb = half * 32; cb < nch; cb += 64) {                   // warp-uniform block loop
+      const int cn = c + 64;
+      int n0 = 0, n1 = 0;
+      if (cn < nch) { n0 = (int)__ldg(hb + (int64_t)cn * C1); n1 = (int)__ldg(hb + (int64_t)cn * C1 + 1); }
+      if (c < nch) {
+        const uint4* src = sb + (int64_t)c * cw;
+        const int q1 = (o1 + 7) >> 3;
+        for (int q = o0 >> 3; q < q1; q += 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (q + u < q1) ? k0b_ldg16(src + q + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (q + u < q1) clear8(v[u], q + u, o0, o1);
+        }
+      }
+      c = cn; o0 = n0; o1 = n1;
     }
   }
   __syncthreads();

@@ -1490,8 +1490,9 @@ struct K0bScratch {
   uint16_t* hdr = nullptr;       // [group][nchunks][C + 1]
   int64_t group = 0, ld_stage = 0, nchunks = 0;
   int C = 0;
-  int threads = K0B_THREADS;     // sort CTA size; a chunk is 16 ids per thread
-  int64_t chunk() const { return (int64_t)threads * K0B_IDS; }
+  int threads = K0B_THREADS;     // sort CTA size
+  int ids = K0B_IDS;             // ids per thread: 16, or 8 with 512-thread CTAs (SPAI_K0B_IDS=8: same 4096-id chunk, more warps)
+  int64_t chunk() const { return (int64_t)threads * ids; }
 };
 // sort CTA size: SPAI_K0B_THREADS=256|512 (A/B); 256-thread CTAs need C <= 256
 static inline int k0b_threads(int64_t C) {
@@ -1563,6 +1564,9 @@ static int64_t k0b_group(int64_t bc, int64_t T, int64_t C) {
 static void k0b_plan(const Pattern& P, int64_t bc, int64_t T, K0bScratch* sc) {
   sc->C = (int)ceil_div(P.E, (int64_t)1 << K0B_SEG_SHIFT);
   sc->threads = k0b_threads(sc->C);
+  // SPAI_K0B_IDS=8: 512-thread sort CTAs with 8 ids per thread (same 4096-id chunk, 1536 threads per SM): measured SLOWER
+  // (cfg3 sort 2.54 -> 3.53 ms, cfg5 3.64 -> 5.08 ms: twice the per-warp counter arrays to zero and scan); kept for A/B
+  { const char* e = getenv("SPAI_K0B_IDS"); sc->ids = (e && atoi(e) == 8) ? 8 : K0B_IDS; if (sc->ids == 8) sc->threads = 512; }
   sc->nchunks = ceil_div(T, sc->chunk());
   sc->ld_stage = sc->nchunks * sc->chunk();
   sc->group = k0b_group(bc, T, sc->C);
@@ -1623,7 +1627,7 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
   } else if (sc && sc->stage && k0b_applies(P, T)) {
     const int C = sc->C;
     const int TH = sc->threads;
-    const size_t ssm = k0b_sort_smem(C, TH);
+    const size_t ssm = k0b_sort_smem(C, TH, sc->ids);
     const size_t bsm = (size_t)std::min<int64_t>((int64_t)K0B_R, C) * K0B_SEG_WORDS * 4;
     const int tasks = (int)ceil_div(C, (int64_t)K0B_R);
     const int smax = (int)k0b_sort_smem(K0B_MAX_SEGS, K0B_THREADS);
@@ -1632,7 +1636,15 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
     SPAI_K0B_ATTR(int64_t, false, 512); SPAI_K0B_ATTR(int64_t, true, 512); SPAI_K0B_ATTR(int32_t, false, 512); SPAI_K0B_ATTR(int32_t, true, 512);
     SPAI_K0B_ATTR(int64_t, false, 256); SPAI_K0B_ATTR(int64_t, true, 256); SPAI_K0B_ATTR(int32_t, false, 256); SPAI_K0B_ATTR(int32_t, true, 256);
 #undef SPAI_K0B_ATTR
+#define SPAI_K0B_ATTR8(IDT, MAP) \
+  SPAI_CUDA(cudaFuncSetAttribute(k0b_sort_kernel<IDT, MAP, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax))
+    SPAI_K0B_ATTR8(int64_t, false); SPAI_K0B_ATTR8(int64_t, true); SPAI_K0B_ATTR8(int32_t, false); SPAI_K0B_ATTR8(int32_t, true);
+#undef SPAI_K0B_ATTR8
     SPAI_CUDA(cudaFuncSetAttribute(k0b_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_build2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_build2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_build2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_build3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K0B_R * K0B_SEG_WORDS * 4));
     SPAI_CUDA(cudaMemsetAsync(nnz0, 0, (size_t)bc * 8, st));
     static const bool timing = getenv("SPAI_K0B_TIMING") != nullptr;      // per-pass device times on stderr (diagnostic)
     cudaEvent_t ev[3] = {};
@@ -1647,16 +1659,38 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
 #define SPAI_K0B_SORT(IDT, PTR, MAP, THR)                                                                         \
   k0b_sort_kernel<IDT, MAP, THR><<<(unsigned)nblk, THR, ssm, st>>>(PTR + g0 * act_ld, T, act_ld, rl, eslot, P.E, C, \
                                                                    sc->stage, sc->ld_stage, sc->hdr, sc->nchunks)
-#define SPAI_K0B_SORT2(IDT, PTR, MAP) do { if (TH == 256) SPAI_K0B_SORT(IDT, PTR, MAP, 256); else SPAI_K0B_SORT(IDT, PTR, MAP, 512); } while (0)
+#define SPAI_K0B_SORT8(IDT, PTR, MAP)                                                                             \
+  k0b_sort_kernel<IDT, MAP, 512, 8><<<(unsigned)nblk, 512, ssm, st>>>(PTR + g0 * act_ld, T, act_ld, rl, eslot, P.E, C, \
+                                                                      sc->stage, sc->ld_stage, sc->hdr, sc->nchunks)
+#define SPAI_K0B_SORT2(IDT, PTR, MAP) do { if (sc->ids == 8) SPAI_K0B_SORT8(IDT, PTR, MAP); else if (TH == 256) SPAI_K0B_SORT(IDT, PTR, MAP, 256); else SPAI_K0B_SORT(IDT, PTR, MAP, 512); } while (0)
       if (elem == 8) { if (eslot) SPAI_K0B_SORT2(int64_t, a64, true); else SPAI_K0B_SORT2(int64_t, a64, false); }
       else { if (eslot) SPAI_K0B_SORT2(int32_t, a32, true); else SPAI_K0B_SORT2(int32_t, a32, false); }
 #undef SPAI_K0B_SORT2
+#undef SPAI_K0B_SORT8
 #undef SPAI_K0B_SORT
       SPAI_CUDA(cudaGetLastError()); ++*launches;
       if (timing) cudaEventRecord(ev[1], st);
-      k0b_build_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
-          sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
-          reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk());
+      static const int build_v = getenv("SPAI_K0B_BUILD") ? atoi(getenv("SPAI_K0B_BUILD")) : 2;   // 1: first version (A/B)
+      if (build_v == 1)
+        k0b_build_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
+            sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
+            reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk());
+      else if (build_v == 3)
+        k0b_build3_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
+            sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
+            reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk());
+      else {
+        // lanes per (chunk, segment) run from the mean run length chunk / C (SPAI_K0B_LANES overrides, A/B)
+        static const int lanes_forced = getenv("SPAI_K0B_LANES") ? atoi(getenv("SPAI_K0B_LANES")) : 0;
+        const int64_t run = sc->chunk() / std::max(C, 1);
+        const int lanes = (lanes_forced == 1 || lanes_forced == 2 || lanes_forced == 4) ? lanes_forced : (run >= 48 ? 4 : 2);
+#define SPAI_K0B_BUILD2(LN)                                                                          \
+  k0b_build2_kernel<LN><<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(                           \
+      sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,                \
+      reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk())
+        if (lanes == 4) SPAI_K0B_BUILD2(4); else if (lanes == 2) SPAI_K0B_BUILD2(2); else SPAI_K0B_BUILD2(1);
+#undef SPAI_K0B_BUILD2
+      }
       SPAI_CUDA(cudaGetLastError()); ++*launches;
       if (timing) {
         cudaEventRecord(ev[2], st);
