@@ -404,7 +404,7 @@ def reward_kernel_name(ctx, p, mode, B, tmax, dtype=None):
 
 
 def mask_kernel_name(p):
-    return "k0_mask_build_smem_kernel" if (p.num_edges + 31) // 32 * 4 <= 100 * 1024 else "k0b_sort_kernel+k0b_build_kernel"
+    return "k0_mask_build_smem_kernel" if (p.num_edges + 31) // 32 * 4 <= 100 * 1024 else "k0b_sort_kernel+k0b_build2_kernel"
 
 
 def phase_times(ctx, call, flush, nrep):
