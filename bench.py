@@ -903,11 +903,43 @@ def run_b200_arm(args):
                     dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
                 e2e[key] = {"value": world * B * nst / (float(t_e) / 1e3), "ms_per_step": float(t_e) / nst,
                             "h2d_bytes_per_step": int(ctx.last_timing().h2d_bytes), "steps": nst}
+            # the platform's own ceiling in the same run: plain cudaMemcpyAsync of 2 GiB of the same pinned buffer on every
+            # rank at once (no kernel of this repository). N ranks share the box's host links; the e2e rate is read against it.
+            local_gbps, n_el = -1.0, 0
+            try:
+                flat = host.view(-1)
+                n_el = min(flat.numel(), (2 << 30) // 8)
+                scratch = torch.empty(n_el, dtype=torch.int64, device=dev)
+                scratch.copy_(flat[:n_el], non_blocking=True)
+                torch.cuda.synchronize()
+            except Exception:            # no collective inside: every rank reaches the barriers below
+                scratch = None
+            barrier()
+            if scratch is not None:
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(2):
+                    scratch.copy_(flat[:n_el], non_blocking=True)
+                p1.record()
+                torch.cuda.synchronize()
+                local_gbps = 2 * n_el * 8 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+            barrier()
+            gbps = torch.tensor([local_gbps], dtype=torch.float64, device=dev)
+            g_min, g_sum = gbps.clone(), gbps.clone()
+            if world > 1:
+                dist.all_reduce(g_min, op=dist.ReduceOp.MIN)
+                dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+            probe = ({"min_gbps_per_gpu": float(g_min), "aggregate_gbps": float(g_sum), "bytes_per_rank": int(2 * n_el * 8),
+                      "what": "plain cudaMemcpyAsync from the same pinned buffer, all ranks at once"}
+                     if float(g_min) > 0 else {"error": "scratch allocation failed on a rank"})
+            del scratch
             head = e2e.get("with_lengths") or e2e["scan"]
             e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
                    "d2h_bytes_per_step": int(B * 8), "input_bytes_per_step": int(B * T * 8),
                    "ms_per_step": head["ms_per_step"], "per_gpu_value": head["value"] / world,
                    "h2d_gbps_per_gpu": head["h2d_bytes_per_step"] / head["ms_per_step"] / 1e6,
+                   "h2d_aggregate_gbps": world * head["h2d_bytes_per_step"] / head["ms_per_step"] / 1e6,
+                   "platform_h2d_probe": probe,
                    "variants": e2e, "numa": numa,
                    "api": "SpaiContext.reward_batch(pinned host int64 actions[B,T], lengths=int32[B]) -> "
                           "spai_reward_batch_host_len: the valid prefix of every row streams over PCIe straight into "
