@@ -10,7 +10,7 @@ p = synth.make_problem("cfg2"); coo = p.a.tocoo()
 mk = lambda: SpaiContext(p.n, p.edge_row, p.edge_col, p.edge_val, coo.row, coo.col, coo.data)
 ctxs = [mk() for _ in range(4)]
 dev = torch.device("cuda", 0)
-acts = device_trajectories(p.num_edges, 4096, 0, dev)
+acts, lens = device_trajectories(p.num_edges, 4096, 0, dev, 0.5)
 streams = [torch.cuda.Stream() for _ in range(4)]
 
 def timed(fn, n=10):
@@ -23,7 +23,7 @@ def timed(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 def single():
-    ctxs[0].reward_batch(acts, 0.5, "copy", torch.float32)
+    ctxs[0].reward_batch(acts, 0.5, "copy", torch.float32, lengths=lens)
 
 def split(nchunk, stagger_cycles):
     def run():
@@ -35,12 +35,12 @@ def split(nchunk, stagger_cycles):
             s.wait_event(start)
             with torch.cuda.stream(s):
                 if stagger_cycles and i: torch.cuda._sleep(int(stagger_cycles * i))
-                ctxs[i % len(ctxs)].reward_batch(acts[i * step:(i + 1) * step], 0.5, "copy", torch.float32)
+                ctxs[i % len(ctxs)].reward_batch(acts[i * step:(i + 1) * step], 0.5, "copy", torch.float32, lengths=lens[i * step:(i + 1) * step])
         for s in streams[:nchunk]:
             cur.wait_stream(s)
     return run
 
 print("single call           ", timed(single))
 for nchunk in (2, 4):
-    for stag_ms in (0.0, 0.35, 0.7):
+    for stag_ms in (0.0, 0.2, 0.4):
         print(f"{nchunk} chunks, stagger {stag_ms} ms", timed(split(nchunk, stag_ms * 1.9e6)))
