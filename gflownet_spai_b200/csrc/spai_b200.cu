@@ -1670,7 +1670,7 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
 #undef SPAI_K0B_SORT
       SPAI_CUDA(cudaGetLastError()); ++*launches;
       if (timing) cudaEventRecord(ev[1], st);
-      static const int build_v = getenv("SPAI_K0B_BUILD") ? atoi(getenv("SPAI_K0B_BUILD")) : 2;   // 1: first version (A/B)
+      const int build_v = getenv("SPAI_K0B_BUILD") ? atoi(getenv("SPAI_K0B_BUILD")) : 2;   // 1, 3: other versions (A/B, tests); read per call
       if (build_v == 1)
         k0b_build_kernel<<<(unsigned)(gb * tasks), K0B_THREADS, bsm, st>>>(
             sc->stage, sc->ld_stage, sc->hdr, sc->nchunks, C, rl, T, P.E, mask + g0 * W, W,
@@ -1681,7 +1681,7 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
             reinterpret_cast<unsigned long long*>(nnz0 + g0), tasks, (int)sc->chunk());
       else {
         // lanes per (chunk, segment) run from the mean run length chunk / C (SPAI_K0B_LANES overrides, A/B)
-        static const int lanes_forced = getenv("SPAI_K0B_LANES") ? atoi(getenv("SPAI_K0B_LANES")) : 0;
+        const int lanes_forced = getenv("SPAI_K0B_LANES") ? atoi(getenv("SPAI_K0B_LANES")) : 0;
         const int64_t run = sc->chunk() / std::max(C, 1);
         const int lanes = (lanes_forced == 1 || lanes_forced == 2 || lanes_forced == 4) ? lanes_forced : (run >= 48 ? 4 : 2);
 #define SPAI_K0B_BUILD2(LN)                                                                          \

@@ -148,3 +148,34 @@ def test_long_rows_pinned_host_with_and_without_lengths():
     assert np.array_equal(a, dev) and np.array_equal(b, dev)
     assert h2d_len == h2d_scan == 8.0 * float(lens.sum()) + 4.0 * acts.shape[0]
     ctx.close()
+
+
+@pytest.mark.parametrize("build,lanes", [("2", "4"), ("2", "2"), ("2", "1"), ("1", "0"), ("3", "0")])
+def test_build_pass_versions_on_sorted_and_ragged_rows(build, lanes, monkeypatch):
+    """Every version of the K0b build pass (default: 2 with lanes per run from the mean run length) gives the oracle's
+    masks on rows that stress the run walk: sorted ids (one segment gets the whole 4096-id chunk: runs far beyond the
+    words a lane keeps in flight), sorted with duplicates, descending, ragged noise rows, an empty row."""
+    p = synth.make_problem("cfg3", 40 / 64)
+    e = p.num_edges
+    ctx = _ctx(p)
+    tmax = 5 * 8192 + 19
+    acts, _ = _ragged(e, 10, tmax, seed=21)
+    rng = np.random.default_rng(4)
+    acts[1, :] = -1
+    acts[1, :tmax - 1] = np.arange(tmax - 1) * 5
+    acts[2, :] = -1
+    acts[2, :30000] = np.sort(rng.integers(0, e, size=30000))
+    acts[3, :] = -1
+    acts[3, :25000] = e - 1 - 2 * np.arange(25000)
+    acts[4, :] = -1
+    monkeypatch.setenv("SPAI_K0_VARIANT", "bucket")
+    monkeypatch.setenv("SPAI_K0B_BUILD", build)
+    if lanes != "0":
+        monkeypatch.setenv("SPAI_K0B_LANES", lanes)
+    t_acts = torch.from_numpy(acts).cuda()
+    kept = ctx.kept_mask(t_acts).cpu().numpy().astype(bool)
+    for b in range(acts.shape[0]):
+        assert np.array_equal(kept[b], orc.kept_edge_mask(e, acts[b])), f"trajectory {b}"
+    out = ctx.reward_batch(t_acts, 0.5, "copy", torch.float32)
+    assert np.array_equal(out["nnz_m"].cpu().numpy(), kept.sum(axis=1))
+    ctx.close()
