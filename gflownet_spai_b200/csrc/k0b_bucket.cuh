@@ -159,6 +159,148 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   for (int i = tid; i < nvec; i += THREADS) dst[i] = src[i];
 }
 
+// Sort pass, second version (opt-in, SPAI_K0B_SORT=2; measured slower than version 1): PERSISTENT CTAs (one wave) walk the (trajectory, chunk) items grid-stride; the ids of the
+// CTA's NEXT item are already on their way into shared memory (cp.async, one element per copy: rows are element-aligned
+// only) while the current chunk is ranked, scattered and written out, so the HBM stream never pauses for a CTA's compute
+// phases and no CTA starts with an empty pipeline. The chunk body is the one of k0b_sort_kernel (same staged layout).
+inline size_t k0b_sort2_smem(int C, int threads, int elem) {
+  return k0b_sort_smem(C, threads) + (size_t)threads * K0B_IDS * elem;
+}
+template <int BYTES>
+__device__ __forceinline__ void k0b_cp_async(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+template <typename IdT, bool HAS_MAP, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k0b_sort2_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
+                 const int32_t* __restrict__ row_len, const int32_t* __restrict__ edge_slot,
+                 int64_t E, int C, uint16_t* __restrict__ stage, int64_t ld_stage,
+                 uint16_t* __restrict__ hdr, int64_t nchunks, int64_t total) {
+  constexpr int NWARPS = THREADS / 32, CHUNK = THREADS * K0B_IDS;
+  extern __shared__ __align__(16) uint32_t k0b_sm[];
+  const int C1 = C + 1;                                           // + trash bucket
+  uint32_t* cnt = k0b_sm;                                         // [WARPS][C1] counters, then bases
+  uint16_t* stg = reinterpret_cast<uint16_t*>(k0b_sm + ((NWARPS * C1 + 3) & ~3));
+  IdT* buf = reinterpret_cast<IdT*>(stg + CHUNK);                 // the next item's ids (CHUNK * 2 bytes of stg keep it 16-byte aligned)
+  __shared__ uint32_t wtot[NWARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t Eu = (uint32_t)E;                                // E < 2^31 (checked at context creation)
+  const uint32_t buf_addr = (uint32_t)__cvta_generic_to_shared(buf + tid);
+
+  // item w = (trajectory b, chunk): valid when the chunk starts inside the row
+  int64_t b = 0, chunk = 0;
+  int left = 0;
+  auto locate = [&](int64_t w) {                                  // first valid item at or after w (grid-stride), or total
+    while (w < total) {
+      b = w / nchunks;
+      chunk = w - b * nchunks;
+      int64_t len = T;
+      if (row_len) len = min(T, (int64_t)row_len[b]);
+      const int64_t c0 = chunk * CHUNK;
+      if (c0 < len) { left = (int)min(len - c0, (int64_t)CHUNK); return w; }
+      w += gridDim.x;
+    }
+    return w;
+  };
+  auto prefetch = [&]() {                                         // ids of item (b, chunk) -> buf
+    const IdT* row = actions + b * ld + chunk * CHUNK + tid;
+#pragma unroll
+    for (int u = 0; u < K0B_IDS; ++u)
+      if (u * THREADS + tid < left) k0b_cp_async<(int)sizeof(IdT)>(buf_addr + u * THREADS * (uint32_t)sizeof(IdT), row + u * THREADS);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int64_t w = locate(blockIdx.x);
+  if (w < total) prefetch();
+  while (w < total) {
+    const int64_t cb = b, cchunk = chunk;
+    const int cleft = left;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    IdT v[K0B_IDS];
+#pragma unroll
+    for (int u = 0; u < K0B_IDS; ++u) v[u] = (u * THREADS + tid < cleft) ? buf[u * THREADS + tid] : (IdT)-1;
+    for (int i = tid; i < NWARPS * C1; i += THREADS) cnt[i] = 0;
+    __syncthreads();                                              // buf is in registers, counters are zero
+    const int64_t wn = locate(w + gridDim.x);
+    if (wn < total) prefetch();                                   // flies during everything below
+
+    uint32_t key[K0B_IDS];       // slot; 0xffffffff (segment = trash) for ids that match no edge
+    uint32_t pos[K0B_IDS];       // rank inside the (warp, segment) sub-list
+    uint32_t* wc = cnt + warp * C1;
+#pragma unroll
+    for (int u = 0; u < K0B_IDS; ++u) {
+      bool ok;
+      uint32_t lo;
+      if (sizeof(IdT) == 8) {
+        const uint64_t a = (uint64_t)v[u];
+        lo = (uint32_t)a;
+        ok = ((uint32_t)(a >> 32) == 0u) & (lo < Eu);
+      } else {
+        lo = (uint32_t)v[u];
+        ok = lo < Eu;
+      }
+      uint32_t s = lo;
+      if (HAS_MAP) s = (uint32_t)__ldg(edge_slot + (ok ? lo : 0u));
+      const uint32_t seg = ok ? (s >> K0B_SEG_SHIFT) : (uint32_t)C;
+      key[u] = ok ? s : 0xffffffffu;
+      pos[u] = atomicAdd(wc + seg, 1u);
+    }
+    __syncthreads();
+
+    uint32_t tot = 0;
+    if (tid < C) {
+#pragma unroll
+      for (int ww = 0; ww < NWARPS; ++ww) tot += cnt[ww * C1 + tid];
+    }
+    uint32_t inc = tot;                                             // inclusive scan over segments
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total_ids = 0;
+#pragma unroll
+    for (int ww = 0; ww < NWARPS; ++ww) {
+      const uint32_t x = wtot[ww];
+      if (ww < warp) wbase += x;
+      total_ids += x;
+    }
+    const uint32_t segbase = wbase + inc - tot;
+    uint16_t* h = hdr + (cb * nchunks + cchunk) * (int64_t)C1;
+    if (tid < C) {
+      uint32_t run = segbase;
+#pragma unroll
+      for (int ww = 0; ww < NWARPS; ++ww) {
+        const uint32_t x = cnt[ww * C1 + tid];
+        cnt[ww * C1 + tid] = run;
+        run += x;
+      }
+      h[tid] = (uint16_t)segbase;
+    }
+    if (tid == 0) h[C] = (uint16_t)total_ids;
+    if (tid < NWARPS) cnt[tid * C1 + C] = (uint32_t)CHUNK;    // trash ids land behind the chunk (never copied out)
+    __syncthreads();
+
+#pragma unroll
+    for (int u = 0; u < K0B_IDS; ++u) {
+      const uint32_t s = key[u];
+      const uint32_t seg = min(s >> K0B_SEG_SHIFT, (uint32_t)C);
+      const uint32_t at = wc[seg] + ((s == 0xffffffffu) ? 0u : pos[u]);
+      if (at < (uint32_t)CHUNK) stg[at] = (uint16_t)(s & 0xffffu);          // trash ids: nothing behind stg but the next item's ids
+    }
+    __syncthreads();
+
+    uint4* dst = reinterpret_cast<uint4*>(stage + cb * ld_stage + cchunk * CHUNK);
+    const uint4* src = reinterpret_cast<const uint4*>(stg);
+    const int nvec = (int)((total_ids + 7) >> 3);
+    for (int i = tid; i < nvec; i += THREADS) dst[i] = src[i];
+    w = wn;
+  }
+}
+
 // grid = B * tasks_per_b, task = R consecutive segments of one trajectory.
 __global__ void __launch_bounds__(K0B_THREADS)
 k0b_build_kernel(const uint16_t* __restrict__ stage, int64_t ld_stage, const uint16_t* __restrict__ hdr,

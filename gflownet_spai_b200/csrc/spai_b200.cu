@@ -1663,7 +1663,24 @@ static int launch_k0(const Pattern& P, const void* act, int elem, int64_t bc, in
   k0b_sort_kernel<IDT, MAP, 512, 8><<<(unsigned)nblk, 512, ssm, st>>>(PTR + g0 * act_ld, T, act_ld, rl, eslot, P.E, C, \
                                                                       sc->stage, sc->ld_stage, sc->hdr, sc->nchunks)
 #define SPAI_K0B_SORT2(IDT, PTR, MAP) do { if (sc->ids == 8) SPAI_K0B_SORT8(IDT, PTR, MAP); else if (TH == 256) SPAI_K0B_SORT(IDT, PTR, MAP, 256); else SPAI_K0B_SORT(IDT, PTR, MAP, 512); } while (0)
-      if (elem == 8) { if (eslot) SPAI_K0B_SORT2(int64_t, a64, true); else SPAI_K0B_SORT2(int64_t, a64, false); }
+      // SPAI_K0B_SORT=2: persistent CTAs with the next chunk prefetched by cp.async (256-thread CTAs, C <= 256). Measured SLOWER
+      // than the one-CTA-per-chunk kernel (cfg3 2.55 -> 2.93 ms, cfg5 3.64 -> 4.11 ms); kept for A/B only
+      const int sort_v = getenv("SPAI_K0B_SORT") ? atoi(getenv("SPAI_K0B_SORT")) : 1;
+      if (sort_v == 2 && TH == 256 && sc->ids == K0B_IDS) {
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const size_t ssm2 = k0b_sort2_smem(C, 256, elem);
+        const unsigned grid2 = (unsigned)std::min<int64_t>(nblk, (int64_t)sms * 4);
+#define SPAI_K0B_SORTP(IDT, PTR, MAP)                                                                                         \
+  do {                                                                                                                        \
+    SPAI_CUDA(cudaFuncSetAttribute(k0b_sort2_kernel<IDT, MAP, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm2)); \
+    k0b_sort2_kernel<IDT, MAP, 256><<<grid2, 256, ssm2, st>>>(PTR + g0 * act_ld, T, act_ld, rl, eslot, P.E, C, sc->stage,     \
+                                                              sc->ld_stage, sc->hdr, sc->nchunks, nblk);                       \
+  } while (0)
+        if (elem == 8) { if (eslot) SPAI_K0B_SORTP(int64_t, a64, true); else SPAI_K0B_SORTP(int64_t, a64, false); }
+        else { if (eslot) SPAI_K0B_SORTP(int32_t, a32, true); else SPAI_K0B_SORTP(int32_t, a32, false); }
+#undef SPAI_K0B_SORTP
+      } else if (elem == 8) { if (eslot) SPAI_K0B_SORT2(int64_t, a64, true); else SPAI_K0B_SORT2(int64_t, a64, false); }
       else { if (eslot) SPAI_K0B_SORT2(int32_t, a32, true); else SPAI_K0B_SORT2(int32_t, a32, false); }
 #undef SPAI_K0B_SORT2
 #undef SPAI_K0B_SORT8

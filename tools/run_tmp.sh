@@ -1,12 +1,12 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python bench.py --no-configs --no-extras --no-sampler > gpurun_out/probe_n1.json 2> gpurun_out/probe_n1.err; echo "n1 rc=$?"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --no-configs --no-extras --no-sampler > gpurun_out/probe_n2.json 2> gpurun_out/probe_n2.err; echo "n2 rc=$?"
-python - <<PY
-import json
-for n in (1,2):
-    d=json.loads(open(f"gpurun_out/probe_n{n}.json").read().strip().splitlines()[-1])
-    e=d["e2e"]; print(n, d["value"], e["value"], e["h2d_gbps_per_gpu"], e["h2d_aggregate_gbps"], e["platform_h2d_probe"])
-PY
-tail -c 300 gpurun_out/probe_n2.err
+timeout -s KILL 900 python -m pytest tests/test_gpu_k0b.py tests/test_gpu_k0c.py tests/test_gpu_fullsize.py -x -q > gpurun_out/k0b7_pytest.log 2>&1; echo "pytest rc=$?"
+tail -n 2 gpurun_out/k0b7_pytest.log
+for v in 1 2; do
+  for cfg in cfg3 cfg5; do
+    B=1024; [ $cfg != cfg3 ] && B=512
+    SPAI_K0B_SORT=$v SPAI_K0B_TIMING=1 timeout -s KILL 600 python tools/ab_k0.py $cfg $B bucket > gpurun_out/ab_k0b7_${cfg}_s$v.log 2>&1; echo "ab $cfg sort $v rc=$?"
+    grep "k0b\]\|\"input\"" gpurun_out/ab_k0b7_${cfg}_s$v.log | sed 's/"GBps_on_read.*"step_ms"/ step_ms/' | cut -c1-140 | sed -n '4,5p;9,10p;14,15p'
+  done
+done
