@@ -1,12 +1,11 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_k0b.py tests/test_gpu_k0c.py tests/test_gpu_fullsize.py -x -q > gpurun_out/k0b7_pytest.log 2>&1; echo "pytest rc=$?"
-tail -n 2 gpurun_out/k0b7_pytest.log
-for v in 1 2; do
-  for cfg in cfg3 cfg5; do
-    B=1024; [ $cfg != cfg3 ] && B=512
-    SPAI_K0B_SORT=$v SPAI_K0B_TIMING=1 timeout -s KILL 600 python tools/ab_k0.py $cfg $B bucket > gpurun_out/ab_k0b7_${cfg}_s$v.log 2>&1; echo "ab $cfg sort $v rc=$?"
-    grep "k0b\]\|\"input\"" gpurun_out/ab_k0b7_${cfg}_s$v.log | sed 's/"GBps_on_read.*"step_ms"/ step_ms/' | cut -c1-140 | sed -n '4,5p;9,10p;14,15p'
-  done
-done
+S=$(date +%s)
+timeout 1200 python bench.py > gpurun_out/r2q_bench.json 2> gpurun_out/r2q_bench.err; echo "bench rc=$? wall=$(( $(date +%s) - S )) s"
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r2q_bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e"]["platform_h2d_probe"])
+for c,v in d["configs"].items(): print(c, {m:round(x["ms_per_step"],2) for m,x in v["variants"].items()})
+PY
