@@ -99,8 +99,8 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
     }
     uint32_t s = lo;
     if (HAS_MAP) s = (uint32_t)__ldg(edge_slot + (ok ? lo : 0u));
-    const uint32_t seg = ok ? (s >> K0B_SEG_SHIFT) : (uint32_t)C;
-    key[u] = ok ? s : 0xffffffffu;
+    key[u] = ok ? s : 0xffffffffu;                                  // `ok` dies here: 16 live predicates cost a packed register
+    const uint32_t seg = min(key[u] >> K0B_SEG_SHIFT, (uint32_t)C);
     pos[u] = atomicAdd(wc + seg, 1u);
   }
   __syncthreads();
@@ -242,8 +242,8 @@ k0b_sort2_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
       }
       uint32_t s = lo;
       if (HAS_MAP) s = (uint32_t)__ldg(edge_slot + (ok ? lo : 0u));
-      const uint32_t seg = ok ? (s >> K0B_SEG_SHIFT) : (uint32_t)C;
-      key[u] = ok ? s : 0xffffffffu;
+      key[u] = ok ? s : 0xffffffffu;                                // `ok` dies here: 16 live predicates cost a packed register
+      const uint32_t seg = min(key[u] >> K0B_SEG_SHIFT, (uint32_t)C);
       pos[u] = atomicAdd(wc + seg, 1u);
     }
     __syncthreads();
