@@ -106,40 +106,46 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   __syncthreads();
 
   // exclusive scan in (segment, warp) order: thread s owns segment s (C <= THREADS); the trash
-  // bucket is left out
-  uint32_t tot = 0;
-  if (tid < C) {
+  // bucket is left out. Only the warps that own segments take part (C = 64: two of eight).
+  const int nwc = (C + 31) >> 5;
+  __shared__ uint32_t s_total;
+  uint32_t tot = 0, inc = 0;
+  if (warp < nwc) {
+    if (tid < C) {
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) tot += cnt[w * C1 + tid];
-  }
-  uint32_t inc = tot;                                             // inclusive scan over segments
+      for (int w = 0; w < NWARPS; ++w) tot += cnt[w * C1 + tid];
+    }
+    inc = tot;                                                    // inclusive scan over segments
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += x;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
+    }
+    if (lane == 31) wtot[warp] = inc;
   }
-  if (lane == 31) wtot[warp] = inc;
   __syncthreads();
-  uint32_t wbase = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < NWARPS; ++w) {
-    const uint32_t x = wtot[w];
-    if (w < warp) wbase += x;
-    total += x;
-  }
-  const uint32_t segbase = wbase + inc - tot;
-  uint16_t* h = hdr + (b * nchunks + chunk) * (int64_t)C1;
-  if (tid < C) {
-    uint32_t run = segbase;
+  if (warp < nwc) {
+    uint32_t wbase = 0, tsum = 0;
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
-      const uint32_t x = cnt[w * C1 + tid];
-      cnt[w * C1 + tid] = run;
-      run += x;
+      const uint32_t x = (w < nwc) ? wtot[w] : 0u;
+      if (w < warp) wbase += x;
+      tsum += x;
     }
-    h[tid] = (uint16_t)segbase;
+    const uint32_t segbase = wbase + inc - tot;
+    uint16_t* h = hdr + (b * nchunks + chunk) * (int64_t)C1;
+    if (tid < C) {
+      uint32_t run = segbase;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) {
+        const uint32_t x = cnt[w * C1 + tid];
+        cnt[w * C1 + tid] = run;
+        run += x;
+      }
+      h[tid] = (uint16_t)segbase;
+    }
+    if (tid == 0) { h[C] = (uint16_t)tsum; s_total = tsum; }
   }
-  if (tid == 0) h[C] = (uint16_t)total;
   if (tid < NWARPS) cnt[tid * C1 + C] = (uint32_t)CHUNK;    // trash ids land behind the chunk (never copied out)
   __syncthreads();
 
@@ -155,7 +161,7 @@ k0b_sort_kernel(const IdT* __restrict__ actions, int64_t T, int64_t ld,
   // sorted chunk -> stage[b][c0 ..): 16-byte stores (ld_stage is a multiple of 8, c0 of 8192)
   uint4* dst = reinterpret_cast<uint4*>(stage + b * ld_stage + c0);
   const uint4* src = reinterpret_cast<const uint4*>(stg);
-  const int nvec = (int)((total + 7) >> 3);
+  const int nvec = (int)((s_total + 7) >> 3);
   for (int i = tid; i < nvec; i += THREADS) dst[i] = src[i];
 }
 
