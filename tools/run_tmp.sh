@@ -1,10 +1,14 @@
 #!/bin/bash
+# final check of the committed state: full GPU suite, smoke, the default bench line
 cd /root/repo
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_k0b.py tests/test_gpu_k0c.py tests/test_gpu_fullsize.py -x -q > gpurun_out/k0b8_pytest.log 2>&1; echo "pytest rc=$?"
-tail -n 1 gpurun_out/k0b8_pytest.log
-for cfg in cfg3 cfg5; do
-  B=1024; [ $cfg != cfg3 ] && B=512
-  SPAI_K0B_TIMING=1 timeout -s KILL 600 python tools/ab_k0.py $cfg $B bucket > gpurun_out/ab_k0b8_${cfg}.log 2>&1; echo "ab $cfg rc=$?"
-  grep "k0b\]\|\"input\"" gpurun_out/ab_k0b8_${cfg}.log | sed 's/"GBps_on_read.*"step_ms"/ step_ms/' | cut -c1-140 | sed -n '4,5p;14,15p'
-done
+timeout -s KILL 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2r_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 1 gpurun_out/r2r_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2r_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 1 gpurun_out/r2r_smoke.log
+S=$(date +%s)
+timeout 1200 python bench.py > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err; echo "bench rc=$? wall=$(( $(date +%s) - S )) s"
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r2r_bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"])
+for c,v in d["configs"].items(): print(c, {m:(round(x["ms_per_step"],2), round(x["k0_frac_of_hbm_peak_on_valid_bytes"],3)) for m,x in v["variants"].items()}, v["parity_check"])
+PY
