@@ -432,9 +432,15 @@ k0b_build2_kernel(const uint16_t* __restrict__ stage, int64_t ld_stage, const ui
                    "r"(span), "r"(seg_addr + ((id[i] >> 3) & 0x1ffcu)), "r"(~(1u << (id[i] & 31u)))
                    : "memory");
   };
-  auto header = [&](int c, int& start, int& end) {                  // the lane's own run bounds: two adjacent 16-bit entries
+  auto header = [&](int c, int& start, int& end) {                  // run bounds of (chunk c, segment seg0 + grp)
     start = 0; end = 0;
-    if (live && c < nch) {
+    if (L == 4) {                                                   // one chunk per warp: lanes 0..8 fetch its nine entries once
+      int o = 0;
+      if (c < nch && lane <= nseg) o = (int)__ldg(hb - grp + (int64_t)c * C1 + lane);
+      start = __shfl_sync(0xffffffffu, o, grp);
+      end = __shfl_sync(0xffffffffu, o, grp + 1);
+      if (!live) end = start;
+    } else if (live && c < nch) {                                   // the lane's own two adjacent 16-bit entries
       start = (int)__ldg(hb + (int64_t)c * C1);
       end = (int)__ldg(hb + (int64_t)c * C1 + 1);
     }
