@@ -774,14 +774,24 @@ def run_b200_arm(args):
         ev[s][1].record()
     barrier()
     wall = time.perf_counter() - wall0
+    # the timed region lasts ~20 ms and the NVML thread catches 1-10 samples in it: the same step keeps running untimed
+    # (a fixed count, so every rank issues the same collectives) while the sampler goes on; both counts are reported
+    n_in_region = len(sampler.sm)
+    for _ in range(2 * args.steps):
+        flush.zero_()
+        step_dev()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = n_in_region
     if world > 1:
         allc = [None] * world
         dist.all_gather_object(allc, clocks)
         sm = [c["sm_mhz"] for c in allc if c and c["sm_mhz"]]
         clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clocks["sm_max_mhz"],
                   "reasons": sorted({r for c in allc if c for r in c["reasons"]}),
-                  "samples": sum(c["samples"] for c in allc if c), "per_rank_sm_mhz": [c["sm_mhz"] if c else None for c in allc]}
+                  "samples": sum(c["samples"] for c in allc if c),
+                  "samples_in_timed_region": sum(c.get("samples_in_timed_region", 0) for c in allc if c),
+                  "per_rank_sm_mhz": [c["sm_mhz"] if c else None for c in allc]}
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     if os.environ.get("SPAI_BENCH_DEBUG"):
         print(f"[rank {rank}] T={T} valid={valid_ids} clocks={clocks}", file=sys.stderr, flush=True)
